@@ -1,0 +1,137 @@
+"""BatchedBaseEnvironment: the reference's plugin surface (colosseumrl/BaseEnvironment.py:10-283), stepping a
+whole batch of independent games per call.
+
+Method names, argument order and the order of return values are the reference's; Python objects become
+tensors on the environment's CUDA device:
+
+=====================  ==============================  ===============================================
+reference               type there                       here (B = batch, P = players)
+=====================  ==============================  ===============================================
+state                   opaque object                    opaque ``*BatchState`` (bit-packed int32 tensor)
+players / new_players   List[int]                        uint8 [B] bit mask (bit p = player p acts next)
+actions                 List[str]                        integer tensor (per game; see each class)
+rewards                 List[float] / ndarray            int8 [B, P] (Tron) or int8 [B] (mover's reward)
+terminal                bool                             uint8 [B] (0 / 1)
+winners                 List[int] | None                 uint8 [B] bit mask (0 = None / nobody)
+ranking                 Dict[int, int]                   uint8 [B, P]
+=====================  ==============================  ===============================================
+
+``is_terminal`` does not exist in the reference (terminal is next_state's 4th return value); here it reads the
+flag the step kernel fused into the state.  All compute happens in libcolosseum_b200.so (hand-written sm_100a
+kernels); there is no CPU or PyTorch fallback path.
+"""
+from abc import ABC, abstractmethod
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib
+
+
+class BatchedBaseEnvironment(ABC):
+    def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
+                 first_env_id: int = 0):
+        self._config = config
+        self.batch = int(batch)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CrlError("colosseumrl_b200 runs on CUDA devices only (no CPU fallback); got %r" % (device,))
+        if not torch.cuda.is_available():
+            raise _lib.CrlError("no CUDA device available (colosseumrl_b200 has no CPU fallback)")
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        self._lib = _lib.init(index)
+        self.seed = int(seed)
+        self.auto_reset = bool(auto_reset)
+        self.first_env_id = int(first_env_id)     # global id of env 0 of this shard (Philox counter)
+        self.stats = torch.zeros(_lib.NSTAT, dtype=torch.int64, device=self.device)
+
+    # -- helpers ------------------------------------------------------------------------------------
+    @property
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check(self, rc):
+        _lib.check(rc, self._lib)
+
+    def _dev(self, t, dtype):
+        """Move an action tensor to the device (non-blocking from pinned host memory)."""
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(t)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    @property
+    def flags(self):
+        return _lib.FLAG_AUTO_RESET if self.auto_reset else 0
+
+    # -- reference surface --------------------------------------------------------------------------
+    @property
+    @abstractmethod
+    def min_players(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def max_players(self) -> int: ...
+
+    @staticmethod
+    @abstractmethod
+    def observation_names() -> List[str]: ...
+
+    @property
+    @abstractmethod
+    def observation_shape(self) -> Dict[str, tuple]: ...
+
+    @abstractmethod
+    def new_state(self, num_players: int = None) -> Tuple[object, torch.Tensor]: ...
+
+    @abstractmethod
+    def next_state(self, state, players, actions): ...
+
+    @abstractmethod
+    def valid_actions(self, state, player): ...
+
+    @abstractmethod
+    def is_valid_action(self, state, player, action): ...
+
+    @abstractmethod
+    def state_to_observation(self, state, player: int) -> Dict[str, torch.Tensor]: ...
+
+    @abstractmethod
+    def is_terminal(self, state) -> torch.Tensor: ...
+
+    def compute_ranking(self, state, players, winners) -> torch.Tensor:
+        """Default (BaseEnvironment.py:173-195): winners rank 0, everybody else 1. uint8 [B, P]."""
+        P = self.max_players
+        bits = (winners.to(torch.int32)[:, None] >> torch.arange(P, device=winners.device)[None]) & 1
+        return (1 - bits).to(torch.uint8)
+
+    @staticmethod
+    def serializable() -> bool:
+        return True
+
+    @staticmethod
+    def serialize_state(state) -> bytes:
+        import io
+        buf = io.BytesIO()
+        torch.save(state, buf)
+        return buf.getvalue()
+
+    @staticmethod
+    def deserialize_state(serialized_state: bytes):
+        import io
+        return torch.load(io.BytesIO(serialized_state), weights_only=False)
+
+    # -- statistics (fused into the step kernels) ----------------------------------------------------
+    def reset_stats(self):
+        self.stats.zero_()
+
+    def all_reduce_stats(self) -> torch.Tensor:
+        """Sum the episode statistics over all ranks (the only collective of the engine)."""
+        out = self.stats.clone()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM)
+        return out

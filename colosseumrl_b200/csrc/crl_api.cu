@@ -1,0 +1,221 @@
+// C ABI of libcolosseum_b200.so (see include/colosseum_b200.h).  Thin launchers only: argument checks,
+// grid sizing, kernel launch on the caller's stream, error capture.  No allocation, no synchronisation.
+#ifdef CRL_HOSTSIM
+#include "cuda_shim.h"
+#endif
+#include "crl_common.cuh"
+#include "philox.cuh"
+#include "tron.cuh"
+#include "../../include/colosseum_b200.h"
+
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+static int check_launch(const char *what) {
+#ifndef CRL_HOSTSIM
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return CRL_ERR_CUDA;
+    }
+#endif
+    return CRL_OK;
+}
+
+static inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" {
+
+int crl_version(void) { return 100; }
+const char *crl_last_error(void) { return g_err; }
+
+int crl_init(int device) {
+#ifndef CRL_HOSTSIM
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(CRL_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(CRL_ERR_ARG, "bad device index%s");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(CRL_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(CRL_ERR_UNSUPPORTED, "libcolosseum_b200 is built for sm_100a only (device is %s)", prop.name);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(CRL_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+#endif
+    return CRL_OK;
+}
+
+int crl_philox_words(uint32_t *out, uint64_t seed, uint64_t first_env, uint32_t step, uint32_t tag, int64_t B,
+                     crl_stream_t stream) {
+    if (!out || B < 0) return fail(CRL_ERR_ARG, "crl_philox_words: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(philox_words_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint4 *)out, (crl_u64)seed,
+               (crl_u64)first_env, step, tag, (long long)B);
+    return check_launch("philox_words_kernel");
+}
+
+/* ------------------------------------------------------------------------------------------- Tron */
+
+static int tron_check(int N, int P, int64_t B) {
+    if (N < 5 || N * N > 64 * TRON_WORDS || N > 255) return fail(CRL_ERR_UNSUPPORTED, "tron: board size must satisfy 5 <= N <= 19%s");
+    if (P < 2 || P > 4) return fail(CRL_ERR_UNSUPPORTED, "tron: player count must satisfy 2 <= P <= 4%s");
+    if (B < 0) return fail(CRL_ERR_ARG, "tron: negative batch%s");
+    return CRL_OK;
+}
+
+// generate_start_positions (TronGridEnvironment.py:183-226) with ring_offset = 1 and the deterministic
+// spawn_offset = 2 of new_state (:228, :222-224).  The ring one cell in from the wall is listed row-major,
+// cut into four sides by the reference's slices, walked clockwise, split into P arcs (np.array_split) and
+// the element `len//2 + 2` (clamped) of each arc is the spawn.
+static int tron_starts(int N, int P, int32_t *heads, int32_t *dirs) {
+    const int half = N / 2, odd = N % 2;
+    const double center = -0.5 * (odd - 1);
+    const int r_in = half - 2, r_out = half - 1, side = 2 * (r_in + 1);
+    if (side <= 0) return CRL_ERR_ARG;
+    std::vector<int> ring_rm;
+    for (int iy = 0; iy < N; iy++)
+        for (int ix = 0; ix < N; ix++) {
+            double y = iy - half + center, x = ix - half + center;
+            bool inner = (x <= r_in && x >= -r_in && y <= r_in && y >= -r_in);
+            bool outer = (x <= r_out && x >= -r_out && y <= r_out && y >= -r_out);
+            if (inner != outer) ring_rm.push_back(iy * N + ix);
+        }
+    auto slice = [&](int start, int stop, int step) {
+        std::vector<int> r;
+        int L = (int)ring_rm.size();
+        for (int i = start < L ? start : L; i < (stop < L ? stop : L); i += step) r.push_back(ring_rm[i]);
+        return r;
+    };
+    std::vector<int> top = slice(0, side, 1), right = slice(side, 3 * side, 2);
+    std::vector<int> bottom = slice(3 * side, 1 << 30, 1), left = slice(side + 1, 3 * side + 1, 2);
+    std::vector<int> loop(top);
+    loop.insert(loop.end(), right.begin(), right.end());
+    loop.insert(loop.end(), bottom.rbegin(), bottom.rend());
+    loop.insert(loop.end(), left.rbegin(), left.rend());
+    auto arc = [&](int len, int p, int &begin, int &size) {  // np.array_split bounds
+        int q = len / P, r = len % P;
+        size = q + (p < r ? 1 : 0);
+        begin = p * q + (p < r ? p : r);
+    };
+    for (int p = 0; p < P; p++) {
+        int b, s;
+        arc((int)loop.size(), p, b, s);
+        if (s <= 0) return CRL_ERR_ARG;
+        int i = s / 2 + 2;
+        heads[p] = loop[b + (i > s - 1 ? s - 1 : i)];
+        arc(4 * side, p, b, s);
+        if (s <= 0) return CRL_ERR_ARG;
+        i = s / 2 + 2;
+        int di = b + (i > s - 1 ? s - 1 : i);
+        dirs[p] = (di / side + 2) % 4;
+    }
+    return CRL_OK;
+}
+
+static int tron_params(int N, int P, TronParams &prm) {
+    int32_t heads[4] = {0, 0, 0, 0}, dirs[4] = {0, 0, 0, 0};
+    if (tron_starts(N, P, heads, dirs) != CRL_OK) return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N/P%s");
+    prm.N = N; prm.P = P; prm.start_dirs = 0;
+    for (int p = 0; p < 4; p++) {
+        prm.start_head[p] = p < P ? (uint32_t)(heads[p] % N) | (uint32_t)(heads[p] / N) << 8 : 0;
+        prm.start_dirs |= (p < P ? (uint32_t)dirs[p] : 0u) << (2 * p);
+        for (int w = 0; w < TRON_WORDS; w++)
+            prm.start_pl[p][w] = (p < P && (heads[p] >> 6) == w) ? 1ull << (heads[p] & 63) : 0ull;
+    }
+    return CRL_OK;
+}
+
+int64_t crl_tron_state_bytes(int N, int P, int64_t B) {
+    if (tron_check(N, P, B)) return -1;
+    return (int64_t)TRON_VEC * 16 * B;
+}
+
+int crl_tron_start_positions(int N, int P, int32_t *heads, int32_t *directions) {
+    int rc = tron_check(N, P, 0);
+    if (rc) return rc;
+    if (!heads || !directions) return fail(CRL_ERR_ARG, "crl_tron_start_positions: null pointer%s");
+    if (tron_starts(N, P, heads, directions)) return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N/P%s");
+    return CRL_OK;
+}
+
+int crl_tron_reset(void *state, const uint8_t *mask, int64_t B, int N, int P, crl_stream_t stream) {
+    int rc = tron_check(N, P, B);
+    if (rc) return rc;
+    if (!state) return fail(CRL_ERR_ARG, "crl_tron_reset: null state%s");
+    TronParams prm;
+    if ((rc = tron_params(N, P, prm))) return rc;
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(tron_reset_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (uint4 *)state, mask, (long long)B, prm);
+    return check_launch("tron_reset_kernel");
+}
+
+int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, int64_t *stats,
+                  int64_t B, int N, int P, int flags, crl_stream_t stream) {
+    int rc = tron_check(N, P, B);
+    if (rc) return rc;
+    if (!state_in || !state_out || !actions || !result) return fail(CRL_ERR_ARG, "crl_tron_step: null pointer%s");
+    TronParams prm;
+    if ((rc = tron_params(N, P, prm))) return rc;
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(tron_step_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (const uint4 *)state_in,
+               (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags);
+    return check_launch("tron_step_kernel");
+}
+
+int crl_tron_policy_random(int8_t *actions, uint64_t seed, uint64_t first_env, uint32_t step, int64_t B,
+                           crl_stream_t stream) {
+    if (!actions || B < 0) return fail(CRL_ERR_ARG, "crl_tron_policy_random: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(tron_policy_random_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint32_t *)actions,
+               (long long)B, (crl_u64)seed, (crl_u64)first_env, step);
+    return check_launch("tron_policy_random_kernel");
+}
+
+int crl_tron_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed, uint64_t first_env,
+                     uint32_t step0, int K, int64_t B, int N, int P, crl_stream_t stream) {
+    int rc = tron_check(N, P, B);
+    if (rc) return rc;
+    if (!state || K < 0) return fail(CRL_ERR_ARG, "crl_tron_rollout: bad argument%s");
+    TronParams prm;
+    if ((rc = tron_params(N, P, prm))) return rc;
+    if (B == 0 || K == 0) return CRL_OK;
+    CRL_LAUNCH(tron_rollout_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (uint4 *)state, (uint2 *)result,
+               (crl_u64 *)stats, (long long)B, prm, (crl_u64)seed, (crl_u64)first_env, step0, K);
+    return check_launch("tron_rollout_kernel");
+}
+
+int crl_tron_observe(const void *state, int player, int8_t *board, int32_t *heads, int32_t *directions,
+                     int32_t *deaths, uint8_t *terminal, int64_t B, int N, int P, crl_stream_t stream) {
+    int rc = tron_check(N, P, B);
+    if (rc) return rc;
+    if (!state || !board || player >= P) return fail(CRL_ERR_ARG, "crl_tron_observe: bad argument%s");
+    TronParams prm;
+    if ((rc = tron_params(N, P, prm))) return rc;
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(tron_observe_kernel, blocks_for(B * N * N, 256), 256, (cudaStream_t)stream, (const uint4 *)state,
+               (long long)B, prm, player, board, heads, directions, deaths, terminal);
+    return check_launch("tron_observe_kernel");
+}
+
+int crl_tron_pack(void *state, const int8_t *board, const int32_t *heads, const int32_t *directions,
+                  const int32_t *deaths, int64_t B, int N, int P, crl_stream_t stream) {
+    int rc = tron_check(N, P, B);
+    if (rc) return rc;
+    if (!state || !board || !heads || !directions || !deaths) return fail(CRL_ERR_ARG, "crl_tron_pack: null pointer%s");
+    TronParams prm;
+    if ((rc = tron_params(N, P, prm))) return rc;
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(tron_pack_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (uint4 *)state, (long long)B, prm,
+               board, heads, directions, deaths);
+    return check_launch("tron_pack_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""BatchedTronGridEnvironment: drop-in batched counterpart of the reference's TronGridEnvironment
+(colosseumrl/envs/tron/TronGridEnvironment.py:61-508), backed by csrc/tron.cuh."""
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from .base import BatchedBaseEnvironment
+from . import _lib
+
+
+def parse_tron_config(config: str):
+    """Same config string as the reference: "N;P;window;remove_on_death" (TronGridEnvironment.py:28-58)."""
+    if len(config) == 0:
+        return 19, 4, -1, False
+
+    def parse(inp):
+        try:
+            return int(inp)
+        except ValueError:
+            return inp.lower() == "true"
+
+    options = list(map(parse, config.split(";")))
+    defaults = [None, 4, -1, False]
+    while len(options) < 4:
+        options.append(defaults[len(options)])
+    return options
+
+
+@dataclass
+class TronBatchState:
+    packed: torch.Tensor                    # int32 [13, B, 4]: SoA of 16-byte vectors, 208 B per environment
+    result: Optional[torch.Tensor] = None   # uint8 [B, 8] written by the step that produced this state
+
+
+class BatchedTronGridEnvironment(BatchedBaseEnvironment):
+    # action codes == TronGridEnvironment.STRING_TO_ACTION (:62-67)
+    STRING_TO_ACTION = {"": 0, "forward": 0, "right": 1, "left": -1}
+    ACTIONS = ["forward", "right", "left"]
+
+    def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
+                 first_env_id: int = 0):
+        super().__init__(config, batch, device, seed, auto_reset, first_env_id)
+        self.N, self.num_players, self.observation_window, self.remove_on_death = parse_tron_config(config)
+        if self._lib.crl_tron_state_bytes(self.N, self.num_players, self.batch) < 0:
+            raise _lib.CrlError(self._lib.crl_last_error().decode())
+
+    @property
+    def min_players(self) -> int:
+        return self.num_players
+
+    @property
+    def max_players(self) -> int:
+        return self.num_players
+
+    @staticmethod
+    def observation_names() -> List[str]:
+        return ["board", "heads", "directions", "deaths"]
+
+    @property
+    def observation_shape(self) -> Dict[str, tuple]:
+        return {"board": (self.N, self.N), "heads": (self.num_players,), "directions": (self.num_players,),
+                "deaths": (self.num_players,)}
+
+    def _alloc(self):
+        return torch.empty((13, self.batch, 4), dtype=torch.int32, device=self.device)
+
+    def new_state(self, num_players: int = None, out: Optional[TronBatchState] = None):
+        """TronGridEnvironment.new_state (:228-263) for every environment of the batch."""
+        assert num_players is None or num_players == self.num_players, \
+            "Do not change the number of players from the game configuration."
+        packed = out.packed if out is not None else self._alloc()
+        self._check(self._lib.crl_tron_reset(packed.data_ptr(), None, self.batch, self.N, self.num_players, self._stream))
+        players = torch.full((self.batch,), (1 << self.num_players) - 1, dtype=torch.uint8, device=self.device)
+        return TronBatchState(packed), players
+
+    def reset_where(self, state: TronBatchState, mask: torch.Tensor):
+        mask = self._dev(mask, torch.uint8)
+        self._check(self._lib.crl_tron_reset(state.packed.data_ptr(), mask.data_ptr(), self.batch, self.N,
+                                             self.num_players, self._stream))
+        return state
+
+    def next_state(self, state: TronBatchState, players, actions, out: Optional[TronBatchState] = None):
+        """TronGridEnvironment.next_state (:265-323).  actions: int8 [B, 4] (0 forward, 1 right, -1 left; entries of
+        dead players ignored).  `players` is accepted for signature parity and ignored (dense action tensor).
+        Returns (new_state, new_players mask, rewards int8 [B, P], terminal uint8 [B], winners mask uint8 [B])."""
+        actions = self._dev(actions, torch.int8)
+        if actions.shape != (self.batch, 4):
+            raise ValueError("actions must have shape [B, 4]")
+        new = out if out is not None else TronBatchState(self._alloc())
+        if new.result is None:
+            new.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
+        self._check(self._lib.crl_tron_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
+                                            new.result.data_ptr(), self.stats.data_ptr(), self.batch, self.N,
+                                            self.num_players, self.flags, self._stream))
+        r = new.result
+        return new, r[:, 5], r[:, :self.num_players].view(torch.int8), r[:, 4], r[:, 6]
+
+    def valid_actions(self, state, player):
+        """Always ['forward', 'right', 'left'] (:325-341): uint8 [B, 3] of ones."""
+        return torch.ones((self.batch, 3), dtype=torch.uint8, device=self.device)
+
+    def is_valid_action(self, state, player, action):
+        return torch.ones((self.batch,), dtype=torch.uint8, device=self.device)
+
+    def is_terminal(self, state: TronBatchState) -> torch.Tensor:
+        if state.result is not None:
+            return state.result[:, 4]
+        return ((state.packed[12, :, 2] >> 20) & 1).to(torch.uint8)
+
+    def compute_ranking(self, state: TronBatchState, players=None, winners=None) -> torch.Tensor:
+        """TronGridEnvironment.compute_ranking (:483-508), fused into the step: uint8 [B, P]."""
+        if state.result is None:
+            raise ValueError("ranking is produced by next_state; this state has not been stepped yet")
+        rk = state.result[:, 7].to(torch.int32)
+        shifts = 2 * torch.arange(self.num_players, device=self.device)
+        return ((rk[:, None] >> shifts[None]) & 3).to(torch.uint8)
+
+    def state_to_observation(self, state: TronBatchState, player: int) -> Dict[str, torch.Tensor]:
+        """TronGridEnvironment.state_to_observation (:363-405); player = -1 gives the absolute (unrotated) state."""
+        B, N, P = self.batch, self.N, self.num_players
+        board = torch.empty((B, N, N), dtype=torch.int8, device=self.device)
+        heads, dirs, deaths = (torch.empty((B, P), dtype=torch.int32, device=self.device) for _ in range(3))
+        self._check(self._lib.crl_tron_observe(state.packed.data_ptr(), int(player), board.data_ptr(), heads.data_ptr(),
+                                               dirs.data_ptr(), deaths.data_ptr(), None, B, N, P, self._stream))
+        return {"board": board, "heads": heads, "directions": dirs, "deaths": deaths}
+
+    def state_from_arrays(self, board, heads, directions, deaths) -> TronBatchState:
+        """Import reference-layout arrays (board [B,N,N], heads = y*N+x, directions, deaths [B,P])."""
+        st = TronBatchState(self._alloc())
+        b, h = self._dev(board, torch.int8), self._dev(heads, torch.int32)
+        d, de = self._dev(directions, torch.int32), self._dev(deaths, torch.int32)
+        self._check(self._lib.crl_tron_pack(st.packed.data_ptr(), b.data_ptr(), h.data_ptr(), d.data_ptr(),
+                                            de.data_ptr(), self.batch, self.N, self.num_players, self._stream))
+        return st
+
+    # -- random policy / fused rollouts (benchmark + self-play helpers) -------------------------------
+    def random_actions(self, step: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = out if out is not None else torch.empty((self.batch, 4), dtype=torch.int8, device=self.device)
+        self._check(self._lib.crl_tron_policy_random(out.data_ptr(), self.seed, self.first_env_id, int(step),
+                                                     self.batch, self._stream))
+        return out
+
+    def rollout(self, state: TronBatchState, step0: int, K: int) -> TronBatchState:
+        """K random-policy steps with auto-reset in one launch (state updated in place)."""
+        if state.result is None:
+            state.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
+        self._check(self._lib.crl_tron_rollout(state.packed.data_ptr(), state.result.data_ptr(), self.stats.data_ptr(),
+                                               self.seed, self.first_env_id, int(step0), int(K), self.batch, self.N,
+                                               self.num_players, self._stream))
+        return state

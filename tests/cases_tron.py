@@ -1,0 +1,195 @@
+"""Tron parity cases, written once against the C ABI and run on both backends (tests/backends.py)."""
+import glob
+import os
+
+import numpy as np
+
+from oracle import oracle as orc
+from colosseumrl_b200 import philox
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def unpack_result(res):
+    """uint8 [B,8] -> dict"""
+    res = np.asarray(res).view(np.uint8).reshape(-1, 8)
+    rk = res[:, 7]
+    return dict(rewards=res[:, :4].view(np.int8).astype(np.int64), terminal=res[:, 4].astype(bool),
+                alive=res[:, 5].astype(np.int64), winners=res[:, 6].astype(np.int64),
+                ranking=np.stack([(rk >> (2 * p)) & 3 for p in range(4)], axis=1).astype(np.int64))
+
+
+def tron_pack(be, N, P, board, heads, dirs, deaths):
+    B = board.shape[0]
+    st = be.zeros((13, B, 4), np.int32)
+    b, h, d, de = (be.upload(np.ascontiguousarray(board, np.int8)), be.upload(np.ascontiguousarray(heads, np.int32)),
+                   be.upload(np.ascontiguousarray(dirs, np.int32)), be.upload(np.ascontiguousarray(deaths, np.int32)))
+    be.check(be.lib.crl_tron_pack(be.ptr(st), be.ptr(b), be.ptr(h), be.ptr(d), be.ptr(de), B, N, P, be.stream))
+    return st
+
+
+def tron_unpack(be, st, N, P, player=-1):
+    B = st.shape[1]
+    board = be.zeros((B, N, N), np.int8)
+    heads, dirs, deaths = (be.zeros((B, P), np.int32) for _ in range(3))
+    term = be.zeros((B,), np.uint8)
+    be.check(be.lib.crl_tron_observe(be.ptr(st), player, be.ptr(board), be.ptr(heads), be.ptr(dirs), be.ptr(deaths),
+                                     be.ptr(term), B, N, P, be.stream))
+    return tuple(be.download(x) for x in (board, heads, dirs, deaths, term))
+
+
+def tron_step(be, st, actions, N, P, flags=0, stats=None, out=None):
+    B = st.shape[1]
+    act = np.zeros((B, 4), np.int8)
+    act[:, :actions.shape[1]] = actions
+    a = be.upload(act)
+    res = be.zeros((B, 8), np.uint8)
+    out = be.zeros((13, B, 4), np.int32) if out is None else out
+    be.check(be.lib.crl_tron_step(be.ptr(st), be.ptr(out), be.ptr(a), be.ptr(res), be.ptr(stats), B, N, P, flags, be.stream))
+    return out, unpack_result(be.download(res))
+
+
+def case_start_positions(be):
+    for N in range(5, 20):
+        for P in (2, 3, 4):
+            h = (np.zeros(4, np.int32), np.zeros(4, np.int32))
+            import ctypes as C
+            be.check(be.lib.crl_tron_start_positions(N, P, h[0].ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     h[1].ctypes.data_as(C.POINTER(C.c_int32))))
+            oh, od = orc.tron_start_positions(N, P)
+            assert (h[0][:P] == oh).all() and (h[1][:P] == od).all(), (N, P)
+
+
+def case_reset(be):
+    for N, P in [(19, 4), (9, 4), (7, 3), (8, 2), (15, 4), (19, 2), (6, 4), (5, 2)]:
+        B = 70
+        st = be.zeros((13, B, 4), np.int32)
+        be.check(be.lib.crl_tron_reset(be.ptr(st), None, B, N, P, be.stream))
+        board, heads, dirs, deaths, term = tron_unpack(be, st, N, P)
+        ob, oh, od, ode = orc.tron_new_state(N, P)
+        assert (board == ob[None]).all() and (heads == oh[None]).all() and (dirs == od[None]).all()
+        assert (deaths == 0).all() and (term == 0).all()
+
+
+def _golden_files():
+    out = []
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "tron_N*_P*.npz"))):
+        g = np.load(path)
+        if int(g["N"]) <= 19 and int(g["P"]) <= 4:
+            out.append(path)
+    return out
+
+
+def case_golden_steps(be, path):
+    """Every recorded (state, actions) -> (next state, outputs) transition of the real reference, as one batch."""
+    g = np.load(path)
+    N, P = int(g["N"]), int(g["P"])
+    T = len(g["t"])
+    s0 = orc.tron_new_state(N, P)
+    first = g["t"] == 0
+    prev = lambda name, init: np.where(first.reshape((-1,) + (1,) * (g[name].ndim - 1)),
+                                       init[None], np.concatenate([init[None], g[name][:-1]], 0))
+    st = tron_pack(be, N, P, prev("board", s0[0]), prev("heads", s0[1]), prev("directions", s0[2]), prev("deaths", s0[3]))
+    out, res = tron_step(be, st, g["actions"], N, P)
+    board, heads, dirs, deaths, term = tron_unpack(be, out, N, P)
+    assert (board == g["board"]).all() and (heads == g["heads"]).all()
+    assert (dirs == g["directions"]).all() and (deaths == g["deaths"]).all()
+    assert (res["rewards"][:, :P] == g["rewards"]).all() and (res["terminal"] == g["terminal"]).all()
+    assert (term.astype(bool) == g["terminal"]).all()
+    assert (res["alive"] == g["alive"]).all() and (res["winners"] == g["winners"]).all()
+    assert (res["ranking"][:, :P] == g["ranking"]).all()
+    # observations (state_to_observation) for every player on the sampled states
+    idx = g["obs_idx"]
+    sub = tron_pack(be, N, P, g["board"][idx], g["heads"][idx], g["directions"][idx], g["deaths"][idx])
+    for p in range(P):
+        ob, oh, od, ode, _ = tron_unpack(be, sub, N, P, player=p)
+        sel = np.arange(len(idx)) * P + p
+        assert (ob == g["obs_board"][sel]).all() and (oh == g["obs_heads"][sel]).all()
+        assert (od == g["obs_directions"][sel]).all() and (ode == g["obs_deaths"][sel]).all()
+
+
+def case_adversarial(be):
+    g = np.load(os.path.join(GOLDEN, "tron_adversarial.npz"))
+    for N in (5, 6, 7):
+        for P in (2, 3, 4):
+            m = (g["N"] == N) & (g["P"] == P)
+            if not m.any():
+                continue
+            st = tron_pack(be, N, P, g["board"][m][:, :N, :N], g["heads"][m][:, :P], g["directions"][m][:, :P], g["deaths"][m][:, :P])
+            out, res = tron_step(be, st, g["actions"][m][:, :P], N, P)
+            board, heads, dirs, deaths, term = tron_unpack(be, out, N, P)
+            assert (board == g["o_board"][m][:, :N, :N]).all() and (heads == g["o_heads"][m][:, :P]).all()
+            assert (dirs == g["o_directions"][m][:, :P]).all() and (deaths == g["o_deaths"][m][:, :P]).all()
+            assert (res["rewards"][:, :P] == g["o_rewards"][m][:, :P]).all()
+            assert (res["terminal"] == g["o_terminal"][m]).all() and (res["alive"] == g["o_alive"][m]).all()
+            assert (res["winners"] == g["o_winners"][m]).all()
+            exp = g["o_ranking"][m][:, :P]
+            ok = exp >= 0   # players owning no cell are absent from the reference's Counter (hand-built states only)
+            assert (res["ranking"][:, :P][ok] == exp[ok]).all()
+
+
+def case_rollout_vs_oracle(be, N=19, P=4, B=200, K=48, seed=5, env0=1000):
+    """policy + step (auto-reset, stats) K times == oracle rollout; and the fused rollout kernel == both."""
+    ob = orc.TronBatch(B, N, P)
+    ob.rollout(seed, env0, 0, K, fresh=True)
+    st = be.zeros((13, B, 4), np.int32)
+    st2 = be.zeros((13, B, 4), np.int32)
+    stats = be.zeros((32,), np.int64)
+    act = be.zeros((B, 4), np.int8)
+    res = be.zeros((B, 8), np.uint8)
+    be.check(be.lib.crl_tron_reset(be.ptr(st), None, B, N, P, be.stream))
+    cur, nxt = st, st2
+    for t in range(K):
+        be.check(be.lib.crl_tron_policy_random(be.ptr(act), seed, env0, t, B, be.stream))
+        if t == 3:
+            r = philox.env_step_words(seed, env0 + np.arange(B), t, philox.TAG_TRON)
+            exp = np.array([0, 1, -1], np.int8)[(r % 3).astype(np.int64)]
+            assert (be.download(act) == exp).all()
+        be.check(be.lib.crl_tron_step(be.ptr(cur), be.ptr(nxt), be.ptr(act), be.ptr(res), be.ptr(stats), B, N, P, 1, be.stream))
+        cur, nxt = nxt, cur
+    board, heads, dirs, deaths, term = tron_unpack(be, cur, N, P)
+    assert (board == ob.board).all() and (heads == ob.heads).all() and (dirs == ob.directions).all()
+    assert (deaths == ob.deaths).all() and (term == ob.terminal).all()
+    s = be.download(stats)
+    assert (s == ob.stats).all(), (s, ob.stats)
+    # fused K-step kernel, split in two launches
+    st3 = be.zeros((13, B, 4), np.int32)
+    stats3 = be.zeros((32,), np.int64)
+    be.check(be.lib.crl_tron_reset(be.ptr(st3), None, B, N, P, be.stream))
+    be.check(be.lib.crl_tron_rollout(be.ptr(st3), None, be.ptr(stats3), seed, env0, 0, K // 3, B, N, P, be.stream))
+    be.check(be.lib.crl_tron_rollout(be.ptr(st3), be.ptr(res), be.ptr(stats3), seed, env0, K // 3, K - K // 3, B, N, P, be.stream))
+    assert (be.download(st3) == be.download(cur)).all()
+    assert (be.download(stats3) == ob.stats).all()
+
+
+def case_in_place_and_masked_reset(be, N=9, P=4, B=67):
+    st = be.zeros((13, B, 4), np.int32)
+    be.check(be.lib.crl_tron_reset(be.ptr(st), None, B, N, P, be.stream))
+    rng = np.random.RandomState(0)
+    ref = be.zeros((13, B, 4), np.int32)
+    be.check(be.lib.crl_tron_reset(be.ptr(ref), None, B, N, P, be.stream))
+    for t in range(6):
+        a = rng.randint(-1, 2, size=(B, 4)).astype(np.int8)
+        ref, _ = tron_step(be, ref, a, N, P)
+        st, _ = tron_step(be, st, a, N, P, out=st)       # in place
+    assert (be.download(st) == be.download(ref)).all()
+    mask = (rng.rand(B) < 0.5).astype(np.uint8)
+    m = be.upload(mask)
+    be.check(be.lib.crl_tron_reset(be.ptr(st), be.ptr(m), B, N, P, be.stream))
+    board, heads, dirs, deaths, term = tron_unpack(be, st, N, P)
+    rb, rh, rd, rde, rt = tron_unpack(be, ref, N, P)
+    nb = orc.tron_new_state(N, P)
+    for e in range(B):
+        if mask[e]:
+            assert (board[e] == nb[0]).all() and (heads[e] == nb[1]).all() and (deaths[e] == 0).all()
+        else:
+            assert (board[e] == rb[e]).all() and (heads[e] == rh[e]).all() and (deaths[e] == rde[e]).all()
+
+
+def case_errors(be):
+    st = be.zeros((13, 4, 4), np.int32)
+    assert be.lib.crl_tron_reset(be.ptr(st), None, 4, 25, 4, be.stream) == 3      # N too large
+    assert be.lib.crl_tron_reset(be.ptr(st), None, 4, 19, 6, be.stream) == 3      # P too large
+    assert b"player count" in be.lib.crl_last_error()
+    assert be.lib.crl_tron_reset(None, None, 4, 19, 4, be.stream) == 1
+    assert be.lib.crl_tron_reset(be.ptr(st), None, 0, 19, 4, be.stream) == 0      # empty batch is fine
