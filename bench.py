@@ -3,19 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tron|ttt4|blokus] [--impl b200|reference]
 
-One "step" = one next_state pass over one batch of environments (the workload's configured batch per GPU).
-N > 1 is launched by torchrun (one rank per GPU, contiguous slices of global environment ids, no data-path
-collective; one NCCL all-reduce of the episode statistics per measurement window).
+One "step" = one next_state pass over ONE batch of environments of the workload's configured size
+(tron: 65,536 envs, the configuration BASELINE.json's metric is quoted on).  N > 1 is launched by torchrun: one
+rank per GPU, each owning a contiguous slice of global environment ids, no data-path collective, one NCCL
+all-reduce of the fused episode statistics per measurement window (weak scaling).
 
-What is timed
-  value  : device-resident.  Per step: [untimed: random-policy action kernel, L2 flush]  ->  CUDA event ->
-           step kernel -> CUDA event.  ms_per_step = mean device time of the step kernel; max over ranks.
-  e2e    : through the public Python API (Batched*Environment.next_state) with HOST buffers: per step the actions
-           are copied from pinned host memory, the step runs, the result record is copied back to pinned host
-           memory (all inside the timed event pair, L2 flushed before it).
-  roofline: algorithmic bytes per env-step x envs / mean step-kernel time vs MEASURED_PEAKS.json.
-  cpu_baseline / --impl reference: the CPU oracle port (oracle/liboracle.so, plain C restatement of the
-           reference's Python; the reference itself is Python and cannot travel to the GPU box) on all host cores.
+How it is timed
+  * L2: the configured batch (13.6 MB of Tron state) would sit in the 126 MB L2, so every rank holds G independent
+    replicas of the batch (>= 4 x L2 of state in total) and consecutive steps cycle through them: each step's
+    state comes from and goes back to HBM ("inputs larger than L2").  No flush kernel is needed.
+  * value: the K timed steps are captured in ONE CUDA graph (the step is a few microseconds, Python launch
+    overhead would dominate) and replayed between two CUDA events on the launching stream; barrier +
+    synchronize on both sides; max over ranks.  ms_per_step = elapsed / K.
+  * e2e: through the public Python API (Batched*Environment.next_state) with HOST buffers: per step the actions
+    are copied from pinned host memory, the step runs, the result record is copied back to pinned host memory and
+    the host waits for it (the loop an actor with a host-side policy runs).
+  * roofline: algorithmic bytes per env-step x envs per launch / mean launch duration
+    (elapsed / K, so launch gaps count against us) vs the measured copy bandwidth in MEASURED_PEAKS.json.
+  * cpu_baseline / --impl reference: the CPU oracle port (oracle/liboracle.so: plain-C restatement of the
+    reference's Python -- the reference itself is Python and cannot travel to the GPU box) on all host cores.
 """
 import argparse
 import json
@@ -30,17 +36,23 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+L2_BYTES = 126 << 20
+
 WORKLOADS = {
-    # name: (description, per-GPU batch, algorithmic bytes per env-step)
-    "tron": ("Tron 4-player 19x19, 65,536 batched envs, random actions (BASELINE.json configs[1])", 65536, 424),
+    # name: description, per-GPU batch, algorithmic bytes per env-step, state bytes per env
+    "tron": dict(desc="Tron 4-player 19x19, 65,536 batched envs, random actions (BASELINE.json configs[1])",
+                 B=65536, bytes=424, state=208, kernel="tron_step_kernel", launches=1),
+    "ttt4": dict(desc="Tic Tac Toe 4-player 3x3x3, 1,048,576 batched envs, random self-play (BASELINE.json configs[3])",
+                 B=1 << 20, bytes=36, state=16, kernel="ttt_rollout_kernel", launches=1),
+    "blokus": dict(desc="Blokus 4-player 20x20, valid_actions + next_state over 16,384 batched games (BASELINE.json configs[2])",
+                   B=16384, bytes=2196, state=352, kernel="blokus_legal_kernel", launches=3),
 }
-FLUSH_BYTES = 512 << 20     # > 126 MB L2
 
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
-        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
@@ -72,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def start(self):
         if self.nv:
@@ -88,37 +100,44 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_tron(B, K, nthreads, seed=0):
+def _cpu_batch(workload, B):
     from oracle import oracle as orc
-    ob = orc.TronBatch(B, 19, 4)
-    ob.rollout(seed, 0, 0, 1, fresh=True, nthreads=nthreads)
-    t0 = time.perf_counter()
-    ob.rollout(seed, 0, 1, K, fresh=False, nthreads=nthreads)
-    dt = time.perf_counter() - t0
-    return B * K / dt, dt
+    if workload == "tron":
+        return orc.TronBatch(B, 19, 4)
+    if workload == "ttt4":
+        return orc.TTTBatch(B, 4)
+    return orc.BlokusBatch(B)
 
 
-def cpu_baseline(workload, target_s=10.0):
+def cpu_baseline(workload, target_s=12.0):
+    """Bounded sample of the same workload on all host cores (C oracle port; K steps per env kept in cache)."""
     from oracle import oracle as orc
     cores = orc.num_threads()
-    B = WORKLOADS[workload][1]
-    fn = {"tron": cpu_tron}[workload]
-    rate, _ = fn(B, 4, cores)
+    B = WORKLOADS[workload]["B"]
+    if workload == "blokus":
+        B = 16 * cores                                   # bounded sample: the CPU needs ~2 ms per Blokus step
+    ob = _cpu_batch(workload, B)
+    ob.rollout(0, 0, 0, 2, fresh=True, nthreads=cores)
+    t0 = time.perf_counter()
+    ob.rollout(0, 0, 2, 4, nthreads=cores)
+    rate = B * 4 / (time.perf_counter() - t0)
     K = max(4, int(rate * target_s / B))
-    rate, dt = fn(B, K, cores)
-    return {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d envs x %d steps (%.1f s) of the C oracle port, %d pthreads" % (B, K, dt, cores)}
+    t0 = time.perf_counter()
+    ob.rollout(0, 0, 6, K, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": B * K / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d envs x %d steps (%.1f s) of the C oracle port of the reference's Python, %d pthreads" % (B, K, dt, cores)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port, all host threads), same config/metric."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU path (oracle port, all host threads), same config / metric / step."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import oracle as orc
-    desc, B, _ = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    B = wl["B"]
     cores = orc.num_threads()
-    ob = orc.TronBatch(B, 19, 4)
+    ob = _cpu_batch(args.workload, B)
     ob.rollout(0, 0, 0, 1, fresh=True, nthreads=cores)
     t = 1
     for _ in range(args.warmup):
@@ -131,20 +150,153 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": desc, "batch_per_step": B, "policy": "philox4x32-10 uniform random",
-                       "note": "reference is Python (cannot travel to the GPU box); this is its plain-C restatement "
-                               "oracle/liboracle.so, which is ~100x faster than the Python original"},
+            "config": {"workload": wl["desc"], "batch_per_step": B, "policy": "philox4x32-10 uniform random, auto-reset",
+                       "note": "the reference is Python + Cython and cannot travel to the GPU box; this arm times its "
+                               "plain-C restatement (oracle/liboracle.so, reference int64 layout) on all host cores -- "
+                               "one step = one next_state pass over the whole batch, as on the GPU arm"},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": "%d envs x %d steps" % (B, args.steps)},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-# ---------------------------------------------------------------------------------------------- GPU arm
+# ---------------------------------------------------------------------------------------------- GPU workloads
+class TronWL:
+    def __init__(self, dev, rank, B, G, K):
+        import torch
+        from colosseumrl_b200.tron import BatchedTronGridEnvironment
+        self.torch, self.B, self.G = torch, B, G
+        # one env object per replica: replica g of rank r owns global env ids [(r*G + g)*B, +B)
+        self.envs = [BatchedTronGridEnvironment("", batch=B, device=dev, seed=0, auto_reset=True,
+                                                first_env_id=(rank * G + g) * B) for g in range(G)]
+        self.states = [e.new_state()[0] for e in self.envs]
+        for e in self.envs[1:]:
+            e.stats = self.envs[0].stats                      # one statistics vector per rank
+        self.local_t = [0] * G
+        self.actions = torch.empty((K, B, 4), dtype=torch.int8, device=dev)   # resident inputs of the timed steps
+        self.h_actions = [torch.from_numpy(np.random.RandomState(rank + i).randint(-1, 2, size=(B, 4)).astype(np.int8)).pin_memory()
+                          for i in range(2)]
+        self.h_result = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
+        self.h2d, self.d2h = B * 4, B * 8
+
+    def prepare(self, k0, K):
+        """Pre-generate the actions of timed steps k0..k0+K-1 (Philox policy kernel), outside the timed region."""
+        lt = list(self.local_t)
+        for k in range(K):
+            g = (k0 + k) % self.G
+            self.envs[g].random_actions(lt[g], out=self.actions[k])
+            lt[g] += 1
+
+    def step(self, k, slot=None):
+        g = k % self.G
+        env, st = self.envs[g], self.states[g]
+        if slot is None:
+            act = env.random_actions(self.local_t[g])
+        else:
+            act = self.actions[slot]
+        self.local_t[g] += 1
+        env.step_(st, act, out=st)                             # in place; C-ABI crl_tron_step
+
+    def e2e_step(self, k):
+        g = k % self.G
+        env, st = self.envs[g], self.states[g]
+        new, _, rewards, terminal, winners = env.next_state(st, None, self.h_actions[k & 1], out=st)   # H2D inside
+        self.h_result.copy_(new.result, non_blocking=True)                                             # D2H
+        self.torch.cuda.current_stream().synchronize()         # the host consumes the result before the next step
+
+    @property
+    def stats_env(self):
+        return self.envs[0]
+
+
+class TTTWL:
+    def __init__(self, dev, rank, B, G, K):
+        import torch
+        from colosseumrl_b200.tictactoe import BatchedTicTacToe4PlayerEnv
+        self.torch, self.B, self.G = torch, B, G
+        self.envs = [BatchedTicTacToe4PlayerEnv("", batch=B, device=dev, seed=0, auto_reset=True,
+                                                first_env_id=(rank * G + g) * B) for g in range(G)]
+        self.states = [e.new_state()[0] for e in self.envs]
+        for e in self.envs[1:]:
+            e.stats = self.envs[0].stats
+        self.local_t = [0] * G
+        self.h_actions = [torch.from_numpy(np.random.RandomState(rank + i).randint(0, 27, size=(B,)).astype(np.int8)).pin_memory()
+                          for i in range(2)]
+        self.h_result = torch.empty((B, 4), dtype=torch.uint8).pin_memory()
+        self.h2d, self.d2h = B, B * 4
+
+    def prepare(self, k0, K):
+        pass
+
+    def step(self, k, slot=None):
+        g = k % self.G
+        self.envs[g].rollout(self.states[g], self.local_t[g], 1)      # policy (in-kernel Philox) + step, one launch
+        self.local_t[g] += 1
+
+    def e2e_step(self, k):
+        g = k % self.G
+        env, st = self.envs[g], self.states[g]
+        new, _, reward, terminal, winners = env.next_state(st, None, self.h_actions[k & 1], out=st)
+        self.h_result.copy_(new.result, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+
+    @property
+    def stats_env(self):
+        return self.envs[0]
+
+
+class BlokusWL:
+    def __init__(self, dev, rank, B, G, K):
+        import torch
+        from colosseumrl_b200.blokus import BatchedBlokusEnvironment
+        self.torch, self.B, self.G = torch, B, G
+        self.envs = [BatchedBlokusEnvironment("", batch=B, device=dev, seed=0, auto_reset=True,
+                                              first_env_id=(rank * G + g) * B, capacity=2048) for g in range(G)]
+        self.states = [e.new_state()[0] for e in self.envs]
+        for e in self.envs[1:]:
+            e.stats = self.envs[0].stats
+        self.local_t = [0] * G
+        self.valid = [(torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B, 2048), dtype=torch.int32, device=dev))
+                      for _ in range(G)]
+        self.act = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(G)]
+        self.h_actions = torch.full((B,), -1, dtype=torch.int32).pin_memory()
+        self.h_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+        self.h_result = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
+        self.h2d, self.d2h = B * 4, B * 8 + B * 4
+
+    def prepare(self, k0, K):
+        pass
+
+    def step(self, k, slot=None):
+        g = k % self.G
+        env, st = self.envs[g], self.states[g]
+        env.valid_actions(st, -1, out=self.valid[g])                  # crl_blokus_legal
+        env.random_actions(self.valid[g], self.local_t[g], out=self.act[g])
+        env.step_(st, self.act[g], out=st)                            # crl_blokus_step
+        self.local_t[g] += 1
+
+    def e2e_step(self, k):
+        # host-side policy sees the counts (D2H), picks "first legal move" on the device-side list via an index
+        # (H2D of one int32 per game), then steps; the result record comes back (D2H).
+        g = k % self.G
+        env, st = self.envs[g], self.states[g]
+        counts, ids = env.valid_actions(st, -1, out=self.valid[g])
+        self.h_counts.copy_(counts, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        idx = self.h_actions.to(env.device, non_blocking=True)        # H2D: the host's choice (here: -1 -> entry 0)
+        act = self.torch.where(counts > 0, ids[:, 0], idx)
+        new, _, reward, terminal, winners = env.next_state(st, None, act, out=st)
+        self.h_result.copy_(new.result, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+
+    @property
+    def stats_env(self):
+        return self.envs[0]
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from colosseumrl_b200.tron import BatchedTronGridEnvironment
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -153,81 +305,69 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    desc, B, bytes_per_step = WORKLOADS[args.workload]
-    K, W = args.steps, args.warmup
+    wl = WORKLOADS[args.workload]
+    B, K, W = wl["B"], args.steps, args.warmup
+    per_replica = wl["state"] * B if args.workload != "blokus" else (wl["state"] + 435 * 4) * B
+    G = args.replicas or max(2, -(-4 * L2_BYTES // per_replica))       # >= 4 x L2 of state per cycle
+    work = {"tron": TronWL, "ttt4": TTTWL, "blokus": BlokusWL}[args.workload](dev, rank, B, G, K)
+    stream = torch.cuda.current_stream(dev)
 
-    env = BatchedTronGridEnvironment("", batch=B, device=dev, seed=0, auto_reset=True, first_env_id=rank * B)
-    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    state, players = env.new_state()
-    spare, _ = env.new_state()
-    actions = torch.empty((B, 4), dtype=torch.int8, device=dev)
-    lib, stream = env._lib, torch.cuda.current_stream(dev)
-
-    def one_step(t, timed):
-        nonlocal state, spare
-        env.random_actions(t, out=actions)
-        flush.fill_(t & 0xff)                                   # evict the state from L2 (untimed)
-        ev0, ev1 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if timed else (None, None)
-        if timed:
-            ev0.record(stream)
-        new, _, _, _, _ = env.next_state(state, None, actions, out=spare)   # the C-ABI call crl_tron_step
-        if timed:
-            ev1.record(stream)
-        state, spare = new, state
-        return ev0, ev1
+    # warm-up (eager launches through the public API), then capture the K timed steps in one CUDA graph
+    k = 0
+    for _ in range(max(W, G)):
+        work.step(k); k += 1
+    torch.cuda.synchronize()
+    work.prepare(k, K)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    cap_stream = torch.cuda.Stream(dev)
+    saved_t = list(work.local_t)
+    with torch.cuda.graph(graph, stream=cap_stream):
+        for j in range(K):
+            work.step(k + j, slot=j)
+    torch.cuda.synchronize()
+    # (capture does not execute: the local step counters advanced, the states did not -- that is what replay does)
 
     clocks = ClockSampler(local)
-    t = 0
-    for _ in range(W):
-        one_step(t, False); t += 1
-    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clocks.start()
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     wall0 = time.perf_counter()
-    evs = []
-    for _ in range(K):
-        evs.append(one_step(t, True)); t += 1
-    ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ar0.record(stream)
-    total_stats = env.all_reduce_stats()                          # the only collective: <= 256 B, once per window
-    ar1.record(stream)
+    ev0.record(stream)
+    graph.replay()
+    ev1.record(stream)
+    total_stats = work.stats_env.all_reduce_stats()                   # the only collective: 256 B, once per window
+    ev2.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    dev_ms = sum(step_ms) + (ar0.elapsed_time(ar1) if world > 1 else 0.0)
-    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    k += K
+    steps_ms = ev0.elapsed_time(ev1)
+    dev_ms = steps_ms + (ev1.elapsed_time(ev2) if world > 1 else 0.0)
+    tmax = torch.tensor([dev_ms, steps_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(tmax.item())
+    dev_ms_max, steps_ms_max = float(tmax[0].item()), float(tmax[1].item())
     ms_per_step = dev_ms_max / K
     value = world * B * K / (dev_ms_max * 1e-3)
-    kernel_ms = sum(step_ms) / K
+    launch_ms = steps_ms_max / K / wl["launches"]
 
-    # ---- end to end through the public API with host buffers (pinned): H2D actions, step, D2H result
-    h_actions = [torch.empty((B, 4), dtype=torch.int8).pin_memory() for _ in range(2)]
-    h_result = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
-    rng = np.random.RandomState(rank)
-    for h in h_actions:
-        h.copy_(torch.from_numpy(rng.randint(-1, 2, size=(B, 4)).astype(np.int8)))
-    e2e_evs = []
-    Ke = min(K, 200)
-    for k in range(W + Ke):
-        flush.fill_(k & 0xff)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        new, _, rewards, terminal, winners = env.next_state(state, None, h_actions[k & 1], out=spare)   # H2D inside
-        h_result.copy_(new.result, non_blocking=True)                                                   # D2H
-        e1.record(stream)
-        e1.synchronize()                    # the host consumes the result before issuing the next step
-        state, spare = new, state
-        if k >= W:
-            e2e_evs.append(e0.elapsed_time(e1))
-    e2e_ms = torch.tensor([sum(e2e_evs)], dtype=torch.float64, device=dev)
+    # ---- end to end through the public API with host buffers
+    Ke = min(K, 100)
+    for j in range(3):
+        work.e2e_step(k); k += 1
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for j in range(Ke):
+        work.e2e_step(k); k += 1
+    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B * Ke / (float(e2e_ms.item()) * 1e-3)
@@ -235,27 +375,34 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        achieved = bytes_per_step * B / (kernel_ms * 1e-3) / 1e9
+        stats = total_stats.cpu().numpy()
+        bytes_per_step = wl["bytes"]
+        if args.workload == "blokus" and stats[0] > 0:
+            # 352 in + 352 out + 4 action + 8 result + 4 count + 4 per listed id (actual mean list length of this run)
+            bytes_per_step = 720 + 4 * float(stats[13]) / float(stats[0])
+        achieved = bytes_per_step * B / (steps_ms_max / K * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         line = {
             "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": B, "policy": "philox4x32-10 uniform random, auto-reset",
-                       "l2": "flushed between timed steps (%d MiB write)" % (FLUSH_BYTES >> 20),
-                       "state_bytes_per_env": 208, "parallelism": "env-sharded x%d, no data-path collective" % world},
+            "warmup": max(W, G), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64" if args.workload == "tron" else "u32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "batch_per_gpu": B, "policy": "philox4x32-10 uniform random, auto-reset",
+                       "l2": "inputs larger than L2: %d independent replicas of the batch per GPU (%.0f MB of state) "
+                             "stepped round-robin, no flush kernel" % (G, G * per_replica / 1e6),
+                       "launch": "K steps captured in one CUDA graph", "state_bytes_per_env": wl["state"],
+                       "parallelism": "env-sharded x%d, no data-path collective, 1 stats all-reduce" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "tron_step_kernel",
-                         "algorithmic_bytes_per_env_step": bytes_per_step, "kernel_ms": kernel_ms},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": B * 8,
-                    "steps": Ke},
-            "gpu_launches": K * world,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": wl["kernel"],
+                         "algorithmic_bytes_per_env_step": bytes_per_step, "launch_ms": launch_ms},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": work.h2d,
+                    "d2h_bytes_per_step": work.d2h, "steps": Ke},
+            "gpu_launches": K * wl["launches"] * world,
             "clocks": clk,
             "wall_s_timed_region": wall,
-            "episodes": int(total_stats[1].item()), "env_steps_counted": int(total_stats[0].item()),
+            "episodes": int(stats[1]), "env_steps_counted": int(stats[0]),
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.workload)
@@ -271,10 +418,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--workload", default="tron", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--replicas", type=int, default=0, help="independent batch replicas per GPU (0 = enough for 4 x L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
+    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
     else:

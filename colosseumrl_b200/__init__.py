@@ -13,4 +13,13 @@ def __getattr__(name):
     if name in ("BatchedTronGridEnvironment", "TronBatchState"):
         from . import tron
         return getattr(tron, name)
+    if name in ("BatchedTicTacToe2PlayerEnv", "BatchedTicTacToe3PlayerEnv", "BatchedTicTacToe4PlayerEnv", "TTTBatchState"):
+        from . import tictactoe
+        return getattr(tictactoe, name)
+    if name in ("BatchedBlokusEnvironment", "BlokusBatchState"):
+        from . import blokus
+        return getattr(blokus, name)
+    if name == "get_environment":
+        from .config import get_environment
+        return get_environment
     raise AttributeError(name)

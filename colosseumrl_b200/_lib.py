@@ -29,6 +29,22 @@ SIGNATURES = {
     "crl_tron_rollout": (_int, [_vp, _vp, _vp, _u64, _u64, _u32, _int, _i64, _int, _int, _vp]),
     "crl_tron_observe": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
     "crl_tron_pack": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
+    "crl_ttt_cells": (_int, [_int]),
+    "crl_ttt_lines": (_int, [_int, C.POINTER(_u32), _int]),
+    "crl_ttt_reset": (_int, [_vp, _vp, _i64, _int, _vp]),
+    "crl_ttt_step": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
+    "crl_ttt_valid_actions": (_int, [_vp, _vp, _i64, _int, _vp]),
+    "crl_ttt_policy_random": (_int, [_vp, _vp, _u64, _u64, _u32, _i64, _int, _int, _vp]),
+    "crl_ttt_rollout": (_int, [_vp, _vp, _vp, _u64, _u64, _u32, _int, _i64, _int, _vp]),
+    "crl_ttt_observe": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _int, _vp]),
+    "crl_ttt_pack": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "crl_blokus_state_bytes": (_i64, [_i64]),
+    "crl_blokus_reset": (_int, [_vp, _vp, _i64, _vp]),
+    "crl_blokus_legal": (_int, [_vp, _int, _vp, _vp, _i32, _vp, _i64, _int, _vp]),
+    "crl_blokus_step": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "crl_blokus_policy_random": (_int, [_vp, _vp, _i32, _vp, _u64, _u64, _u32, _i64, _vp]),
+    "crl_blokus_observe": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "crl_blokus_pack": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 
 

@@ -1,0 +1,150 @@
+"""BatchedBlokusEnvironment: drop-in batched counterpart of BlokusEnvironment
+(colosseumrl/envs/blokus/BlokusEnvironment.py), backed by csrc/blokus.cuh."""
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .base import BatchedBaseEnvironment
+
+PIECE_NAMES = ["monomino1", "domino1", "trominoe1", "trominoe2", "tetrominoes1", "tetrominoes2", "tetrominoes3",
+               "tetrominoes4", "tetrominoes5"] + ["pentominoe%d" % i for i in range(1, 13)]   # board.py:24-44
+ORIENTATIONS = ["north", "northeast", "east", "southeast", "south", "southwest", "west", "northwest"]  # board.py:47
+
+
+def action_to_string(action_id: int) -> str:
+    """Engine action id -> the reference's action string (BlokusEnvironment.py:55-80); -1 -> ''."""
+    if action_id < 0:
+        return ""
+    k, o, cell, piece = action_id % 5, (action_id // 5) % 8, (action_id // 40) % 400, action_id // 16000
+    return "{};{};{}".format(PIECE_NAMES[piece], (cell % 20, cell // 20), ORIENTATIONS[o] + str(k))
+
+
+def string_to_action(action_str: str) -> int:
+    """The reference's action string (BlokusEnvironment.py:83-106) -> engine action id; '' -> -1."""
+    if action_str == "":
+        return -1
+    piece, index, orientation = action_str.split(";")
+    x, y = (int(v) for v in index.replace("(", "").replace(")", "").split(","))
+    return ((PIECE_NAMES.index(piece) * 400 + y * 20 + x) * 8 + ORIENTATIONS.index(orientation[:-1])) * 5 + int(orientation[-1])
+
+
+@dataclass
+class BlokusBatchState:
+    packed: torch.Tensor                        # int32 [B, 22, 4]: 352 bytes per game
+    result: Optional[torch.Tensor] = None       # uint8 [B, 8] of the step that produced this state
+
+
+class BatchedBlokusEnvironment(BatchedBaseEnvironment):
+    def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
+                 first_env_id: int = 0, capacity: int = 2048):
+        super().__init__(config, batch, device, seed, auto_reset, first_env_id)
+        self.capacity = int(capacity)      # slots per game in the valid-action list (reference max observed: 1753)
+
+    @property
+    def min_players(self) -> int:
+        return 4
+
+    @property
+    def max_players(self) -> int:
+        return 4
+
+    @property
+    def observation_shape(self) -> Dict[str, tuple]:
+        return {"board": (20, 20), "pieces": (4, 21), "score": (4,), "player": (1,)}
+
+    @staticmethod
+    def observation_names() -> List[str]:
+        return ["board", "pieces", "score", "player"]
+
+    @staticmethod
+    def all_piece_types() -> List[str]:
+        return PIECE_NAMES
+
+    @staticmethod
+    def all_orientations() -> List[str]:
+        return ORIENTATIONS
+
+    def _alloc(self):
+        return torch.empty((self.batch, 22, 4), dtype=torch.int32, device=self.device)
+
+    def new_state(self, num_players: int = 4, out: Optional[BlokusBatchState] = None):
+        assert num_players in (None, 4)
+        packed = out.packed if out is not None else self._alloc()
+        self._check(self._lib.crl_blokus_reset(packed.data_ptr(), None, self.batch, self._stream))
+        return BlokusBatchState(packed), torch.ones((self.batch,), dtype=torch.uint8, device=self.device)
+
+    def valid_actions(self, state: BlokusBatchState, player: int = -1,
+                      out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """valid_actions (:453-500): (counts int32 [B], ids int32 [B, capacity]) in the reference's order;
+        counts == 0 <=> [''].  player = -1: each game's current mover."""
+        if out is None:
+            out = (torch.empty((self.batch,), dtype=torch.int32, device=self.device),
+                   torch.empty((self.batch, self.capacity), dtype=torch.int32, device=self.device))
+        counts, ids = out
+        self._check(self._lib.crl_blokus_legal(state.packed.data_ptr(), int(player), counts.data_ptr(), ids.data_ptr(),
+                                               ids.shape[1], self.stats.data_ptr(), self.batch, self.flags, self._stream))
+        return counts, ids
+
+    def is_valid_action(self, state: BlokusBatchState, player: int, action) -> torch.Tensor:
+        action = self._dev(action, torch.int32)
+        counts, ids = self.valid_actions(state, player)
+        slot = torch.arange(ids.shape[1], device=self.device)[None]
+        return (((ids == action[:, None]) & (slot < counts[:, None])).any(dim=1) & (action >= 0)).to(torch.uint8)
+
+    def next_state(self, state: BlokusBatchState, players, actions, out: Optional[BlokusBatchState] = None):
+        """next_state (:357-451).  actions: int32 [B] action ids (-1 = pass).
+        Returns (new_state, new_players mask, reward int8 [B] (mover's), terminal uint8 [B], winners mask uint8 [B])."""
+        new = self.step_(state, actions, out)
+        r = new.result
+        return new, (1 << r[:, 4].to(torch.int32)).to(torch.uint8), r[:, 0].view(torch.int8), r[:, 1] & 1, r[:, 2]
+
+    def step_(self, state: BlokusBatchState, actions, out: Optional[BlokusBatchState] = None) -> BlokusBatchState:
+        """The bare crl_blokus_step launch (out may be `state` itself: in place).  Outputs are in new.result."""
+        actions = self._dev(actions, torch.int32)
+        new = out if out is not None else BlokusBatchState(self._alloc())
+        if new.result is None:
+            new.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
+        self._check(self._lib.crl_blokus_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
+                                              new.result.data_ptr(), self.stats.data_ptr(), self.batch, self.flags,
+                                              self._stream))
+        return new
+
+    def is_terminal(self, state: BlokusBatchState) -> torch.Tensor:
+        return ((state.packed[:, 21, 1] >> 16) & 1).to(torch.uint8)
+
+    def current_rewards(self, state: BlokusBatchState) -> torch.Tensor:
+        """Scores per player (BlokusEnvironment.py:340-355): int32 [B, 4]."""
+        s = state.packed[:, 21, 0]
+        return torch.stack([(s >> (8 * p)) & 0xff for p in range(4)], dim=1)
+
+    def state_to_observation(self, state: BlokusBatchState, player: int) -> Dict[str, torch.Tensor]:
+        B = self.batch
+        board = torch.empty((B, 20, 20), dtype=torch.int8, device=self.device)
+        pieces = torch.empty((B, 4, 21), dtype=torch.uint8, device=self.device)
+        score = torch.empty((B, 4), dtype=torch.int32, device=self.device)
+        meta = torch.empty((B, 4), dtype=torch.int32, device=self.device)
+        self._check(self._lib.crl_blokus_observe(state.packed.data_ptr(), int(player), board.data_ptr(), pieces.data_ptr(),
+                                                 score.data_ptr(), meta.data_ptr(), B, self._stream))
+        obs = {"board": board, "pieces": pieces, "score": score,
+               "player": torch.full((B, 1), int(player), dtype=torch.int32, device=self.device)}
+        if player < 0:
+            obs.update(round=meta[:, 0], mover=meta[:, 1], terminal=meta[:, 2], episode_steps=meta[:, 3])
+        return obs
+
+    def state_from_arrays(self, board, pieces, score, round_count, mover) -> BlokusBatchState:
+        st = BlokusBatchState(self._alloc())
+        meta = torch.zeros((self.batch, 4), dtype=torch.int32, device=self.device)
+        meta[:, 0] = self._dev(round_count, torch.int32)
+        meta[:, 1] = self._dev(mover, torch.int32)
+        b, p, s = self._dev(board, torch.int8), self._dev(pieces, torch.uint8), self._dev(score, torch.int32)
+        self._check(self._lib.crl_blokus_pack(st.packed.data_ptr(), b.data_ptr(), p.data_ptr(), s.data_ptr(),
+                                              meta.data_ptr(), self.batch, self._stream))
+        return st
+
+    def random_actions(self, valid, step: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        counts, ids = valid
+        out = out if out is not None else torch.empty((self.batch,), dtype=torch.int32, device=self.device)
+        self._check(self._lib.crl_blokus_policy_random(counts.data_ptr(), ids.data_ptr(), ids.shape[1], out.data_ptr(),
+                                                       self.seed, self.first_env_id, int(step), self.batch, self._stream))
+        return out

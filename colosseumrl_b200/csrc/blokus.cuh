@@ -1,0 +1,401 @@
+// Blokus 4-player 20x20: legal-move generation and move application on row bitboards (sm_100a).
+//
+// Replaces (reference file:line):
+//   Board.get_all_valid_moves        envs/blokus/board.py:170-193  (anchors :114-154, orientation/shift loop :156-168)
+//   check_shifted & friends          envs/blokus/computation.py:145-180, 184-246, 53-142   (numba)
+//   BlokusEnvironment.valid_actions  envs/blokus/BlokusEnvironment.py:453-500 (canonical order of the flattened dict)
+//   BlokusEnvironment.next_state     :357-451  (Board.update_board board.py:87-98, AI.update_player ai.py:44-54,
+//                                    the terminal test `not any(p.check_moves(board, round_count))` :424 which runs on
+//                                    the OLD board / OLD round with the NEW inventories, winners/reward :425-440)
+//   new_state :248-289, state_to_observation :721-768
+//
+// HBM layout: 352 bytes per game, AoS (a warp owns a game): 22 x uint4 = 88 words
+//   w[20*c + y]  row y of colour c's plane, bit x set iff colour c occupies (x, y)           (c = 0..3, 80 words)
+//   w[80 + c]    inventory of player c, bit p set iff piece p (PIECE_TYPES order) is still held
+//   w[84]        scores, one byte per player        w[85] round | mover << 8 | terminal << 16
+//   w[86]        steps taken in this episode        w[87] unused
+// Lanes 0..21 of the warp move the game with one 128-bit access each (352 contiguous bytes).
+//
+// Legality in bitboard form: with
+//   A   = empty & ~N4(own)                                   "allowed" cells (computation.py:122-142, 89-119)
+//   ANC = {corner}            if round == 0 (board.py:177-179)
+//         A & D4(own)         otherwise      (board.py:114-154)
+//   FIT_s[q] = AND_i A[q + cell_i(s)]                       shape s fits with its bounding-box corner at q
+// action (piece, anchor a, orientation o, shift k) is legal  <=>  a in ANC  and  FIT_s[a - cell_k(s)],
+// s = shape(piece, o).  The list is emitted in the reference's order piece -> anchor (row-major) -> o -> k, with
+// lanes = the (o, k) ids of one piece and __ballot_sync / __popc prefix sums for the compaction.
+#pragma once
+#include "crl_common.cuh"
+#include "philox.cuh"
+#include "blokus_tables.h"
+
+#define BLK_WORDS 88
+#define BLK_VEC 22
+#define BLK_WARPS 4            // warps (= games) per CTA
+#define BLK_ROWMASK 0xFFFFFu
+#define BLK_MAX_ANCHORS 400
+
+// per-warp shared scratch
+struct BlkSmem {
+    uint32_t st[BLK_WORDS];          // the game state (old board during a step)
+    uint32_t A[24];                  // allowed rows; rows 20..23 are zero (shapes are at most 5 rows tall)
+    uint32_t anc[20];                // anchor rows
+    uint32_t F[8 * 20];              // FIT boards of the current piece's (<= 8) shapes
+    uint16_t alist[BLK_MAX_ANCHORS]; // anchors, row-major: y*20 + x
+};
+
+__device__ __forceinline__ void blk_load(BlkSmem &sm, const uint4 *__restrict__ st, long long g, int lane) {
+    if (lane < BLK_VEC) {
+        uint4 v = ld_stream(st + g * BLK_VEC + lane);
+        sm.st[4 * lane + 0] = v.x; sm.st[4 * lane + 1] = v.y; sm.st[4 * lane + 2] = v.z; sm.st[4 * lane + 3] = v.w;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void blk_store(const BlkSmem &sm, uint4 *__restrict__ st, long long g, int lane) {
+    __syncwarp();
+    if (lane < BLK_VEC)
+        st_stream(st + g * BLK_VEC + lane,
+                  make_uint4(sm.st[4 * lane + 0], sm.st[4 * lane + 1], sm.st[4 * lane + 2], sm.st[4 * lane + 3]));
+}
+// new_state (BlokusEnvironment.py:248-289): empty board, round 0, four full inventories, player 0 to move
+__device__ __forceinline__ void blk_new_state(BlkSmem &sm, int lane) {
+    __syncwarp();
+    for (int i = lane; i < BLK_WORDS; i += 32) sm.st[i] = (i >= 80 && i < 84) ? ((1u << BLK_NPIECE) - 1u) : 0u;
+    __syncwarp();
+}
+
+// A and ANC rows of player c (0-based) for the board in sm.st; fills sm.A, sm.anc, sm.alist; returns #anchors.
+__device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int round, int lane) {
+    __syncwarp();
+    uint32_t a = 0, an = 0;
+    if (lane < 20) {
+        const int y = lane;
+        uint32_t own = sm.st[20 * c + y];
+        uint32_t occ = sm.st[y] | sm.st[20 + y] | sm.st[40 + y] | sm.st[60 + y];
+        uint32_t up = y > 0 ? sm.st[20 * c + y - 1] : 0u, dn = y < 19 ? sm.st[20 * c + y + 1] : 0u;
+        uint32_t n4 = up | dn | (own << 1) | (own >> 1);                       // is_valid_adjacents
+        a = ~occ & ~n4 & BLK_ROWMASK;                                          // is_valid_cell
+        if (round == 0) {                                                      // PLAYER_DEFAULT_CORNERS (board.py:50)
+            const int cx = (c & 1) ? 19 : 0, cy = (c & 2) ? 19 : 0;
+            an = (y == cy) ? (1u << cx) : 0u;
+        } else {
+            uint32_t d4 = (up << 1) | (up >> 1) | (dn << 1) | (dn >> 1);       // check_valid_corner (board.py:127-154)
+            an = a & d4;
+        }
+    }
+    if (lane < 24) sm.A[lane] = a;
+    if (lane < 20) sm.anc[lane] = an;
+    // row-major anchor list: exclusive prefix of the per-row counts
+    int cnt = __popc(an), pre = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, pre, d);
+        if (lane >= d) pre += t;
+    }
+    int total = __shfl_sync(0xffffffffu, pre, 31);
+    int pos = pre - cnt;
+    while (an) {
+        int x = __ffs((int)an) - 1;
+        an &= an - 1;
+        sm.alist[pos++] = (uint16_t)(lane * 20 + x);
+    }
+    __syncwarp();
+    return total;
+}
+
+// FIT boards of piece p's shapes into sm.F (lanes = rows)
+__device__ __forceinline__ void blk_fit_boards(BlkSmem &sm, int p, int lane) {
+    const int s0 = BLK_PIECE_SHAPE0[p], ns = BLK_PIECE_SHAPE0[p + 1] - s0;
+    __syncwarp();
+    if (lane < 20) {
+        for (int sl = 0; sl < ns; sl++) {
+            uint32_t cells = BLK_SHAPE_CELLS[s0 + sl], f = BLK_ROWMASK;
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                uint32_t cd = cells >> (6 * i);
+                f &= sm.A[lane + ((cd >> 3) & 7)] >> (cd & 7);
+            }
+            sm.F[sl * 20 + lane] = f;
+        }
+    }
+    __syncwarp();
+}
+
+// Enumerate the legal moves of player c holding `inv` on the board in sm.st.
+//   EMIT = true : write action ids (canonical order) to out[0..cap) and return the full count
+//   EMIT = false: return 1 as soon as any move exists, else 0   (AI.check_moves, ai.py:36-42)
+template <bool EMIT>
+__device__ __forceinline__ int blk_enumerate(BlkSmem &sm, int c, int round, uint32_t inv, int lane,
+                                             int32_t *__restrict__ out, int cap) {
+    const int na = blk_allowed_and_anchors(sm, c, round, lane);
+    if (na == 0) return 0;
+    int base = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int p = 0; p < BLK_NPIECE; p++) {
+        if (!(inv >> p & 1u)) continue;
+        blk_fit_boards(sm, p, lane);
+        const int s0 = BLK_PIECE_SHAPE0[p], id0 = BLK_PIECE_ID0[p], nid = BLK_PIECE_ID0[p + 1] - id0;
+        const uint32_t e0 = lane < nid ? BLK_ID_TAB[id0 + lane] : 0u;
+        const uint32_t e1 = lane + 32 < nid ? BLK_ID_TAB[id0 + 32 + lane] : 0u;
+        const int f0 = ((int)(e0 & 127u) - s0) * 20, dx0 = (e0 >> 7) & 7, dy0 = (e0 >> 10) & 7;
+        const int f1 = ((int)(e1 & 127u) - s0) * 20, dx1 = (e1 >> 7) & 7, dy1 = (e1 >> 10) & 7;
+        const bool v0 = lane < nid, v1 = lane + 32 < nid;
+        for (int ai = 0; ai < na; ai++) {
+            const int a = sm.alist[ai], ay = a / 20, ax = a - ay * 20;
+            int qx = ax - dx0, qy = ay - dy0;
+            bool ok0 = v0 && qx >= 0 && qy >= 0 && ((sm.F[f0 + max(qy, 0)] >> max(qx, 0)) & 1u);
+            uint32_t m0 = __ballot_sync(0xffffffffu, ok0), m1 = 0;
+            bool ok1 = false;
+            if (nid > 32) {
+                qx = ax - dx1; qy = ay - dy1;
+                ok1 = v1 && qx >= 0 && qy >= 0 && ((sm.F[f1 + max(qy, 0)] >> max(qx, 0)) & 1u);
+                m1 = __ballot_sync(0xffffffffu, ok1);
+            }
+            if (EMIT) {
+                const int code = (p * 400 + a) * 40;
+                int pos = base + __popc(m0 & lt);
+                if (ok0 && pos < cap) out[pos] = code + (int)(e0 >> 13);
+                base += __popc(m0);
+                pos = base + __popc(m1 & lt);
+                if (ok1 && pos < cap) out[pos] = code + (int)(e1 >> 13);
+                base += __popc(m1);
+            } else if (m0 | m1) {
+                return 1;
+            }
+        }
+    }
+    return base;
+}
+
+// ---- valid_actions: one warp per game.  player < 0: the game's current mover.
+__global__ void __launch_bounds__(32 * BLK_WARPS)
+blokus_legal_kernel(const uint4 *__restrict__ st, int32_t *__restrict__ counts, int32_t *__restrict__ ids, int cap,
+                    crl_u64 *stats, long long B, int player, int flags) {
+    __shared__ BlkSmem smem[BLK_WARPS];
+    __shared__ int sm_stat[CRL_NSTAT];
+    BlockStats bs{sm_stat};
+    if (stats) bs.init();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
+    if (g < B) {
+        BlkSmem &sm = smem[wid];
+        blk_load(sm, st, g, lane);
+        if ((flags & CRL_FLAG_AUTO_RESET) && (sm.st[85] >> 16 & 1u)) blk_new_state(sm, lane);
+        const uint32_t meta = sm.st[85];
+        const int c = player >= 0 ? player : (int)(meta >> 8 & 3u);
+        const int n = blk_enumerate<true>(sm, c, (int)(meta & 0xffu), sm.st[80 + c], lane, ids + g * cap, cap);
+        if (lane == 0) {
+            counts[g] = n;
+            if (stats) atomicAdd(&sm_stat[ST_NVALID], n);
+        }
+    }
+    if (stats) bs.flush(stats);
+}
+
+// ---- next_state: one warp per game.
+// result record, 8 bytes: int8 reward | u8 flags (1 terminal, 2 illegal action, 4 placed) | u8 winners mask |
+//                         u8 ranking bits (bit p = rank of p: winners 0, others 1) | u8 next mover | 3 unused
+__global__ void __launch_bounds__(32 * BLK_WARPS)
+blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, const int32_t *__restrict__ actions,
+                   uint2 *__restrict__ result, crl_u64 *stats, long long B, int flags) {
+    __shared__ BlkSmem smem[BLK_WARPS];
+    __shared__ int sm_stat[CRL_NSTAT];
+    BlockStats bs{sm_stat};
+    if (stats) bs.init();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
+    if (g < B) {
+        BlkSmem &sm = smem[wid];
+        blk_load(sm, in, g, lane);
+        if ((flags & CRL_FLAG_AUTO_RESET) && (sm.st[85] >> 16 & 1u)) blk_new_state(sm, lane);
+        const uint32_t meta = sm.st[85];
+        const int round = (int)(meta & 0xffu), mover = (int)(meta >> 8 & 3u);
+        const int aid = actions[g];
+        uint32_t inv[4] = {sm.st[80], sm.st[81], sm.st[82], sm.st[83]};
+        uint32_t scores = sm.st[84];
+        uint32_t new_row = lane < 20 ? sm.st[20 * mover + lane] : 0u;
+        int error = 0, placed = 0;
+        if (aid >= 0) {
+            // decode ((piece*400 + y*20 + x)*8 + o)*5 + k   (string form: BlokusEnvironment.py:55-106)
+            const int piece = aid / 16000, rem = aid - piece * 16000, cell = rem / 40, ok = rem - cell * 40;
+            const int o = ok / 5, k = ok - o * 5;
+            bool legal = piece < BLK_NPIECE;
+            const int pc = legal ? piece : 0, size = BLK_PIECE_SIZE[pc];
+            uint32_t minv = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) minv |= (q == mover) ? inv[q] : 0u;
+            legal = legal && k < size && (minv >> pc & 1u);
+            const uint32_t e = BLK_ID_TAB[BLK_PIECE_ID0[pc] + (legal ? o * size + k : 0)];
+            const uint32_t cells = BLK_SHAPE_CELLS[e & 127u];
+            const int ay = cell / 20, ax = cell - ay * 20;
+            const int qx = ax - (int)((e >> 7) & 7u), qy = ay - (int)((e >> 10) & 7u);
+            blk_allowed_and_anchors(sm, mover, round, lane);      // validation against A / ANC of the mover
+            legal = legal && qx >= 0 && qy >= 0 && (sm.anc[ay] >> ax & 1u);
+            uint32_t add = 0;
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                const uint32_t cd = cells >> (6 * i);
+                const int x = qx + (int)(cd & 7u), y = qy + (int)((cd >> 3) & 7u);
+                // y <= 23 by construction (rows 20..23 of A are zero), x may exceed 19 -> bit not in A
+                legal = legal && x >= 0 && y >= 0 && x < 20 && (sm.A[min(max(y, 0), 23)] >> max(x, 0) & 1u);
+                add |= (y == lane && x >= 0 && x < 20) ? (1u << x) : 0u;
+            }
+            if (legal) {
+                placed = 1;
+                new_row |= add;                                                     // Board.update_board
+                const uint32_t left = minv & ~(1u << pc);
+                int gain = size + (left == 0 ? (pc == 0 ? 20 : 15) : 0);            // AI.update_player (ai.py:44-54)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (q == mover) {
+                        inv[q] = left;
+                        scores = (scores & ~(0xffu << (8 * q))) | ((((scores >> (8 * q)) & 0xffu) + gain) & 0xffu) << (8 * q);
+                    }
+                }
+            } else {
+                error = 1;                                                          // illegal id: flagged, applied as a pass
+            }
+        }
+        // terminal test on the OLD board / OLD round with the NEW inventories (BlokusEnvironment.py:424)
+        int any = 0;
+#pragma unroll 1
+        for (int q = 0; q < 4 && !any; q++) {
+            uint32_t iq = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) iq |= (r == q) ? inv[r] : 0u;
+            any = blk_enumerate<false>(sm, q, round, iq, lane, nullptr, 0);
+        }
+        const int terminal = !any;
+        int reward = 0, winners = 0;
+        int sc[4] = {(int)(scores & 0xff), (int)(scores >> 8 & 0xff), (int)(scores >> 16 & 0xff), (int)(scores >> 24)};
+        if (terminal) {                                                             // :425-440
+            int mx = max(max(sc[0], sc[1]), max(sc[2], sc[3]));                     // max_score starts at 0, scores >= 0
+            int ms = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) ms |= (q == mover) ? sc[q] : 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                winners |= (sc[q] == mx) ? (1 << q) : 0;
+                reward += (sc[q] < ms || (sc[q] == ms && q < mover)) ? 1 : 0;       // index in the stable ascending sort
+            }
+        }
+        const int nround = round + (mover == 3 ? 1 : 0), nmover = (mover + 1) & 3;  // :446-449
+        const uint32_t ep_len = sm.st[86] + 1u;
+        // commit into the shared copy, then store with 22 x 128-bit lanes
+        __syncwarp();
+        if (lane < 20) sm.st[20 * mover + lane] = new_row;
+        if (lane < 4) sm.st[80 + lane] = lane == 0 ? inv[0] : lane == 1 ? inv[1] : lane == 2 ? inv[2] : inv[3];
+        if (lane == 4) sm.st[84] = scores;
+        if (lane == 5) sm.st[85] = (uint32_t)(nround & 0xff) | (uint32_t)nmover << 8 | (uint32_t)terminal << 16;
+        if (lane == 6) sm.st[86] = ep_len;
+        blk_store(sm, outst, g, lane);
+        if (lane == 0) {
+            const uint32_t rank = 0xfu & ~(uint32_t)winners;
+            result[g] = make_uint2(((uint32_t)reward & 0xffu) | (uint32_t)(terminal | error << 1 | placed << 2) << 8 |
+                                       (uint32_t)winners << 16 | rank << 24,
+                                   (uint32_t)nmover);
+            if (stats) {
+                atomicAdd(&sm_stat[ST_STEPS], 1);
+                if (error) atomicAdd(&sm_stat[ST_ERRORS], 1);
+                if (reward) atomicAdd(&sm_stat[ST_REWARD], (mover + 1) * reward);
+                if (terminal) {
+                    atomicAdd(&sm_stat[ST_EPISODES], 1);
+                    atomicAdd(&sm_stat[ST_EPLEN], (int)ep_len);
+                    if (!winners) atomicAdd(&sm_stat[ST_NOWIN], 1);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (winners >> q & 1) atomicAdd(&sm_stat[ST_WINS + q], 1);
+                        else atomicAdd(&sm_stat[ST_RANK + q], 1);
+                        atomicAdd(&sm_stat[ST_SCORE + q], sc[q]);
+                    }
+                }
+            }
+        }
+    }
+    if (stats) bs.flush(stats);
+}
+
+// uniform random policy over the generated list: the (r0 % n)-th entry, pass (-1) if n == 0
+__global__ void blokus_policy_random_kernel(const int32_t *__restrict__ counts, const int32_t *__restrict__ ids, int cap,
+                                            int32_t *__restrict__ actions, long long B, crl_u64 seed, crl_u64 first_env,
+                                            uint32_t step) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B) return;
+    int n = min(counts[g], cap);
+    uint4 r = env_words(seed, first_env + (crl_u64)g, step, CRL_TAG_BLOKUS);
+    actions[g] = n > 0 ? ids[g * cap + (long long)(r.x % (uint32_t)n)] : -1;
+}
+
+__global__ void blokus_reset_kernel(uint4 *__restrict__ st, const uint8_t *__restrict__ mask, long long B) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * BLK_VEC) return;
+    long long g = idx / BLK_VEC;
+    int v = (int)(idx - g * BLK_VEC);
+    if (mask && !mask[g]) return;
+    const uint32_t full = (1u << BLK_NPIECE) - 1u;
+    st[idx] = (v == 20) ? make_uint4(full, full, full, full) : make_uint4(0, 0, 0, 0);
+}
+
+// state_to_observation (BlokusEnvironment.py:721-768), one thread per output cell.
+//  player >= 0: board int8[B][20][20] of relative player ids (-1 empty) rotated by np.rot90(k=-player);
+//               pieces u8[B][4][21] rows by relative id; score int32[B][4] rolled by -player.
+//  player <  0: absolute unpack: board = Board.board_contents (0 empty, 1..4 colour), pieces / score in seat order.
+//  meta (optional) int32[B][4] = round, mover, terminal, episode steps.
+__global__ void blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, int8_t *__restrict__ board,
+                                      uint8_t *__restrict__ pieces, int32_t *__restrict__ score, int32_t *__restrict__ meta) {
+    const uint32_t *st = (const uint32_t *)st4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * 400) return;
+    long long g = idx / 400;
+    int cell = (int)(idx - g * 400), i = cell / 20, j = cell - i * 20;
+    const uint32_t *s = st + g * BLK_WORDS;
+    int si = i, sj = j;                                     // source cell of np.rot90(k=-player)
+    if (player == 1) { si = 19 - j; sj = i; }
+    else if (player == 2) { si = 19 - i; sj = 19 - j; }
+    else if (player == 3) { si = j; sj = 19 - i; }
+    int v = -1;
+    for (int c = 0; c < 4; c++) v = (s[20 * c + si] >> sj & 1u) ? c : v;
+    if (player >= 0) v = v < 0 ? -1 : ((v - player) & 3);   // _relative_player_id (:46-50)
+    else v = v + 1;
+    board[idx] = (int8_t)v;
+    if (cell < 84) {                                        // pieces[rel][piece]
+        int r = cell / 21, p = cell - r * 21;
+        int src = player >= 0 ? ((r + player) & 3) : r;
+        pieces[g * 84 + cell] = (uint8_t)(s[80 + src] >> p & 1u);
+    }
+    if (cell < 4) {
+        int src = player >= 0 ? ((cell + player) & 3) : cell;
+        score[g * 4 + cell] = (int)(s[84] >> (8 * src) & 0xffu);
+        if (meta) {
+            uint32_t m = s[85];
+            meta[g * 4 + cell] = cell == 0 ? (int)(m & 0xffu) : cell == 1 ? (int)(m >> 8 & 3u)
+                                 : cell == 2 ? (int)(m >> 16 & 1u) : (int)s[86];
+        }
+    }
+}
+
+// import a reference-layout state: board int8[B][20][20] (0..4), inventory u8[B][4][21], scores int32[B][4],
+// meta int32[B][4] = round, mover, terminal, episode steps
+__global__ void blokus_pack_kernel(uint4 *__restrict__ st4, long long B, const int8_t *__restrict__ board,
+                                   const uint8_t *__restrict__ pieces, const int32_t *__restrict__ score,
+                                   const int32_t *__restrict__ meta) {
+    uint32_t *st = (uint32_t *)st4;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * BLK_WORDS) return;
+    long long g = idx / BLK_WORDS;
+    int w = (int)(idx - g * BLK_WORDS);
+    uint32_t v = 0;
+    if (w < 80) {
+        int c = w / 20, y = w - c * 20;
+        for (int x = 0; x < 20; x++) v |= (board[g * 400 + y * 20 + x] == c + 1) ? (1u << x) : 0u;
+    } else if (w < 84) {
+        for (int p = 0; p < BLK_NPIECE; p++) v |= pieces[g * 84 + (w - 80) * 21 + p] ? (1u << p) : 0u;
+    } else if (w == 84) {
+        for (int q = 0; q < 4; q++) v |= ((uint32_t)score[g * 4 + q] & 0xffu) << (8 * q);
+    } else if (w == 85) {
+        v = ((uint32_t)meta[g * 4] & 0xffu) | ((uint32_t)meta[g * 4 + 1] & 3u) << 8 | ((uint32_t)meta[g * 4 + 2] & 1u) << 16;
+    } else if (w == 86) {
+        v = (uint32_t)meta[g * 4 + 3];
+    }
+    st[idx] = v;
+}

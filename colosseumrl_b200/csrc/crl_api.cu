@@ -6,6 +6,8 @@
 #include "crl_common.cuh"
 #include "philox.cuh"
 #include "tron.cuh"
+#include "ttt.cuh"
+#include "blokus.cuh"
 #include "../../include/colosseum_b200.h"
 
 #include <stdio.h>
@@ -216,6 +218,198 @@ int crl_tron_pack(void *state, const int8_t *board, const int32_t *heads, const 
     CRL_LAUNCH(tron_pack_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (uint4 *)state, (long long)B, prm,
                board, heads, directions, deaths);
     return check_launch("tron_pack_kernel");
+}
+
+/* ------------------------------------------------------------------------------------------- Tic Tac Toe */
+
+}  // extern "C" (helpers below are C++)
+
+// Line directions and start masks from the board dimensions (2p 3x3, 3p 3x5, 4p 3x3x3).
+static int ttt_params(int n, TTTParams &prm) {
+    int D[3];
+    if (n == 2) { D[0] = 1; D[1] = 3; D[2] = 3; }
+    else if (n == 3) { D[0] = 1; D[1] = 3; D[2] = 5; }
+    else if (n == 4) { D[0] = 3; D[1] = 3; D[2] = 3; }
+    else return fail(CRL_ERR_UNSUPPORTED, "tictactoe: players must be 2, 3 or 4%s");
+    prm.n = n; prm.cells = D[0] * D[1] * D[2]; prm.cellmask = (1u << prm.cells) - 1u; prm.ndirs = 0;
+    for (int d = 0; d < TTT_MAX_DIRS; d++) { prm.stride[d] = 1; prm.start[d] = 0; }
+    for (int da = 0; da <= 1; da++)
+        for (int db = -1; db <= 1; db++)
+            for (int dc = -1; dc <= 1; dc++) {
+                // canonical sign: first non-zero component positive
+                if (da == 0 && (db < 0 || (db == 0 && dc <= 0))) continue;
+                uint32_t start = 0;
+                for (int a = 0; a < D[0]; a++)
+                    for (int b = 0; b < D[1]; b++)
+                        for (int c = 0; c < D[2]; c++) {
+                            int a2 = a + 2 * da, b2 = b + 2 * db, c2 = c + 2 * dc;
+                            if (a2 < 0 || a2 >= D[0] || b2 < 0 || b2 >= D[1] || c2 < 0 || c2 >= D[2]) continue;
+                            start |= 1u << ((a * D[1] + b) * D[2] + c);
+                        }
+                if (!start) continue;
+                prm.stride[prm.ndirs] = (uint32_t)((da * D[1] + db) * D[2] + dc);
+                prm.start[prm.ndirs] = start;
+                prm.ndirs++;
+            }
+    return CRL_OK;
+}
+
+extern "C" {
+
+int crl_ttt_cells(int n) {
+    TTTParams prm;
+    return ttt_params(n, prm) ? -1 : prm.cells;
+}
+
+int crl_ttt_lines(int n, uint32_t *line_masks, int capacity) {
+    TTTParams prm;
+    if (ttt_params(n, prm)) return -1;
+    int cnt = 0;
+    for (int d = 0; d < prm.ndirs; d++)
+        for (int c = 0; c < prm.cells; c++)
+            if (prm.start[d] >> c & 1) {
+                if (line_masks && cnt < capacity)
+                    line_masks[cnt] = 1u << c | 1u << (c + prm.stride[d]) | 1u << (c + 2 * prm.stride[d]);
+                cnt++;
+            }
+    return cnt;
+}
+
+int crl_ttt_reset(void *state, const uint8_t *mask, int64_t B, int n, crl_stream_t stream) {
+    TTTParams prm;
+    int rc = ttt_params(n, prm);
+    if (rc) return rc;
+    if (!state || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_reset: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(ttt_reset_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint4 *)state, mask, (long long)B);
+    return check_launch("ttt_reset_kernel");
+}
+
+int crl_ttt_step(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, uint32_t *valid_after,
+                 int64_t *stats, int64_t B, int n, int flags, crl_stream_t stream) {
+    TTTParams prm;
+    int rc = ttt_params(n, prm);
+    if (rc) return rc;
+    if (!state_in || !state_out || !actions || !result || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_step: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(ttt_step_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state_in, (uint4 *)state_out,
+               actions, (uint32_t *)result, valid_after, (crl_u64 *)stats, (long long)B, prm, flags);
+    return check_launch("ttt_step_kernel");
+}
+
+int crl_ttt_valid_actions(const void *state, uint32_t *mask, int64_t B, int n, crl_stream_t stream) {
+    TTTParams prm;
+    int rc = ttt_params(n, prm);
+    if (rc) return rc;
+    if (!state || !mask || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_valid_actions: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(ttt_valid_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state, mask, (long long)B, prm);
+    return check_launch("ttt_valid_kernel");
+}
+
+int crl_ttt_policy_random(const void *state, int8_t *actions, uint64_t seed, uint64_t first_env, uint32_t step,
+                          int64_t B, int n, int flags, crl_stream_t stream) {
+    TTTParams prm;
+    int rc = ttt_params(n, prm);
+    if (rc) return rc;
+    if (!state || !actions || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_policy_random: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(ttt_policy_random_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state, actions,
+               (long long)B, prm, flags, (crl_u64)seed, (crl_u64)first_env, step);
+    return check_launch("ttt_policy_random_kernel");
+}
+
+int crl_ttt_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed, uint64_t first_env, uint32_t step0,
+                    int K, int64_t B, int n, crl_stream_t stream) {
+    TTTParams prm;
+    int rc = ttt_params(n, prm);
+    if (rc) return rc;
+    if (!state || B < 0 || K < 0) return fail(CRL_ERR_ARG, "crl_ttt_rollout: bad argument%s");
+    if (B == 0 || K == 0) return CRL_OK;
+    CRL_LAUNCH(ttt_rollout_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint4 *)state, (uint32_t *)result,
+               (crl_u64 *)stats, (long long)B, prm, (crl_u64)seed, (crl_u64)first_env, step0, K);
+    return check_launch("ttt_rollout_kernel");
+}
+
+int crl_ttt_observe(const void *state, int player, int8_t *board, int8_t *winner, int8_t *mover, int64_t B, int n,
+                    crl_stream_t stream) {
+    TTTParams prm;
+    int rc = ttt_params(n, prm);
+    if (rc) return rc;
+    if (!state || !board || B < 0 || player >= n) return fail(CRL_ERR_ARG, "crl_ttt_observe: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(ttt_observe_kernel, blocks_for(B * prm.cells, 256), 256, (cudaStream_t)stream, (const uint4 *)state,
+               (long long)B, prm, player, board, winner, mover);
+    return check_launch("ttt_observe_kernel");
+}
+
+int crl_ttt_pack(void *state, const int8_t *board, const int8_t *winner, const int8_t *mover, int64_t B, int n,
+                 crl_stream_t stream) {
+    TTTParams prm;
+    int rc = ttt_params(n, prm);
+    if (rc) return rc;
+    if (!state || !board || !winner || !mover || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_pack: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(ttt_pack_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint4 *)state, (long long)B, prm, board,
+               winner, mover);
+    return check_launch("ttt_pack_kernel");
+}
+
+/* ------------------------------------------------------------------------------------------- Blokus */
+
+int64_t crl_blokus_state_bytes(int64_t B) { return B < 0 ? -1 : (int64_t)BLK_WORDS * 4 * B; }
+
+int crl_blokus_reset(void *state, const uint8_t *mask, int64_t B, crl_stream_t stream) {
+    if (!state || B < 0) return fail(CRL_ERR_ARG, "crl_blokus_reset: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(blokus_reset_kernel, blocks_for(B * BLK_VEC, 256), 256, (cudaStream_t)stream, (uint4 *)state, mask, (long long)B);
+    return check_launch("blokus_reset_kernel");
+}
+
+int crl_blokus_legal(const void *state, int player, int32_t *counts, int32_t *action_ids, int32_t capacity,
+                     int64_t *stats, int64_t B, int flags, crl_stream_t stream) {
+    if (!state || !counts || !action_ids || capacity <= 0 || B < 0 || player > 3)
+        return fail(CRL_ERR_ARG, "crl_blokus_legal: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(blokus_legal_kernel, blocks_for(B, BLK_WARPS), 32 * BLK_WARPS, (cudaStream_t)stream, (const uint4 *)state,
+               counts, action_ids, (int)capacity, (crl_u64 *)stats, (long long)B, player, flags);
+    return check_launch("blokus_legal_kernel");
+}
+
+int crl_blokus_step(const void *state_in, void *state_out, const int32_t *actions, uint8_t *result, int64_t *stats,
+                    int64_t B, int flags, crl_stream_t stream) {
+    if (!state_in || !state_out || !actions || !result || B < 0) return fail(CRL_ERR_ARG, "crl_blokus_step: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(blokus_step_kernel, blocks_for(B, BLK_WARPS), 32 * BLK_WARPS, (cudaStream_t)stream, (const uint4 *)state_in,
+               (uint4 *)state_out, actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, flags);
+    return check_launch("blokus_step_kernel");
+}
+
+int crl_blokus_policy_random(const int32_t *counts, const int32_t *action_ids, int32_t capacity, int32_t *actions,
+                             uint64_t seed, uint64_t first_env, uint32_t step, int64_t B, crl_stream_t stream) {
+    if (!counts || !action_ids || !actions || capacity <= 0 || B < 0) return fail(CRL_ERR_ARG, "crl_blokus_policy_random: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(blokus_policy_random_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, counts, action_ids, (int)capacity,
+               actions, (long long)B, (crl_u64)seed, (crl_u64)first_env, step);
+    return check_launch("blokus_policy_random_kernel");
+}
+
+int crl_blokus_observe(const void *state, int player, int8_t *board, uint8_t *pieces, int32_t *score, int32_t *meta,
+                       int64_t B, crl_stream_t stream) {
+    if (!state || !board || !pieces || !score || B < 0 || player > 3) return fail(CRL_ERR_ARG, "crl_blokus_observe: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(blokus_observe_kernel, blocks_for(B * 400, 256), 256, (cudaStream_t)stream, (const uint4 *)state, (long long)B,
+               player, board, pieces, score, meta);
+    return check_launch("blokus_observe_kernel");
+}
+
+int crl_blokus_pack(void *state, const int8_t *board, const uint8_t *pieces, const int32_t *score, const int32_t *meta,
+                    int64_t B, crl_stream_t stream) {
+    if (!state || !board || !pieces || !score || !meta || B < 0) return fail(CRL_ERR_ARG, "crl_blokus_pack: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(blokus_pack_kernel, blocks_for(B * BLK_WORDS, 256), 256, (cudaStream_t)stream, (uint4 *)state, (long long)B,
+               board, pieces, score, meta);
+    return check_launch("blokus_pack_kernel");
 }
 
 }  // extern "C"

@@ -1,0 +1,267 @@
+// Generalised Tic Tac Toe (2p 3x3, 3p 3x5, 4p 3x3x3): batched next_state with the win test done as
+// shifted-mask compares, fused with terminal / winners / ranking / valid-action mask (sm_100a).
+//
+// Replaces (reference file:line):
+//   TicTacToe{2,3,4}PlayerEnv.next_state   envs/tictactoe/tictactoe_2p_env.py:240-315, _3p_env.py:241-316,
+//                                          _4p_env.py:271-346 (13 scipy.signal.correlate calls per step for 4p)
+//   valid_actions / is_valid_action        tictactoe_2p_env.py:317-380
+//   new_state                              :139-170
+//   state_to_observation                   :382-407 (+ the "% 3" relabel quirk of tictactoe_4p_env.py:50)
+//
+// HBM layout: ONE 16-byte vector per environment, uint4 state[B]:
+//   .x = cells of player 0 (bit = C-order flat cell index, <= 27 bits) | mover << 27 | (winner + 1) << 29
+//   .y = cells of player 1 | min(episode steps, 31) << 27
+//   .z = cells of player 2,   .w = cells of player 3
+// A warp loads/stores 512 contiguous bytes per instruction; one thread owns one environment.
+//
+// Win test: for every line direction d (4 in 2-D, 13 in 3-D) with flat stride s_d, three in a row exists iff
+//   m & (m >> s_d) & (m >> 2 s_d) & START_d != 0,  START_d = cells where a length-3 segment along d fits.
+// This equals "3 in scipy.signal.correlate(mask, pattern, 'valid')" for the reference's WINNING_SHAPES
+// (checked against the oracle's 8 / 20 / 49 line tables in tests/test_abi.py::test_ttt_line_tables).
+#pragma once
+#include "crl_common.cuh"
+#include "philox.cuh"
+
+#define TTT_MAX_DIRS 13
+
+struct TTTParams {
+    int n;          // players: 2, 3, 4
+    int cells;      // 9, 15, 27
+    int ndirs;
+    uint32_t cellmask;
+    uint32_t stride[TTT_MAX_DIRS];
+    uint32_t start[TTT_MAX_DIRS];
+};
+
+struct TTTEnv {
+    uint32_t m[4];
+    int mover, winner1;  // winner1 = winner + 1, 0 = None
+    uint32_t ep_len;
+};
+
+struct TTTOut {
+    int reward, terminal, error, placed, winners, nvalid;
+    uint32_t valid_after;
+};
+
+__device__ __forceinline__ void ttt_decode(TTTEnv &s, uint4 v) {
+    s.m[0] = v.x & 0x07ffffffu; s.m[1] = v.y & 0x07ffffffu; s.m[2] = v.z & 0x07ffffffu; s.m[3] = v.w & 0x07ffffffu;
+    s.mover = (v.x >> 27) & 3; s.winner1 = (v.x >> 29) & 7;
+    s.ep_len = v.y >> 27;
+}
+__device__ __forceinline__ uint4 ttt_encode(const TTTEnv &s) {
+    return make_uint4(s.m[0] | (uint32_t)s.mover << 27 | (uint32_t)s.winner1 << 29,
+                      s.m[1] | min(s.ep_len, 31u) << 27, s.m[2], s.m[3]);
+}
+__device__ __forceinline__ void ttt_new_state(TTTEnv &s) {
+    s.m[0] = s.m[1] = s.m[2] = s.m[3] = 0; s.mover = 0; s.winner1 = 0; s.ep_len = 0;
+}
+__device__ __forceinline__ bool ttt_is_terminal(const TTTEnv &s, const TTTParams &prm) {
+    return s.winner1 != 0 || ((s.m[0] | s.m[1] | s.m[2] | s.m[3]) == prm.cellmask);
+}
+__device__ __forceinline__ bool ttt_has_line(uint32_t m, const TTTParams &prm) {
+    uint32_t hit = 0;
+#pragma unroll
+    for (int d = 0; d < TTT_MAX_DIRS; d++)
+        if (d < prm.ndirs) hit |= m & (m >> prm.stride[d]) & (m >> (2 * prm.stride[d])) & prm.start[d];
+    return hit != 0;
+}
+
+// next_state (tictactoe_2p_env.py:283-315).  action: C-order flat cell index, negative = '' (pass).
+__device__ __forceinline__ void ttt_step_env(TTTEnv &s, int action, const TTTParams &prm, TTTOut &o) {
+    uint32_t occ = s.m[0] | s.m[1] | s.m[2] | s.m[3];
+    o.nvalid = __popc(~occ & prm.cellmask);
+    bool in_range = action >= 0 && action < prm.cells;
+    uint32_t bit = in_range ? (1u << action) : 0u;
+    bool cell_free = in_range && !(occ & bit);                       // is_valid_action (:350-380)
+    bool placed = cell_free && s.winner1 == 0;                       // :293
+    o.error = (action >= 0 && !cell_free) ? 1 : 0;                   // invalid action: silent no-op in the reference
+    o.placed = placed;
+    if (placed) {
+        uint32_t mine = 0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            s.m[p] |= (p == s.mover) ? bit : 0u;                     // :295
+            mine |= (p == s.mover) ? s.m[p] : 0u;
+        }
+        if (ttt_has_line(mine, prm)) s.winner1 = s.mover + 1;        // :297-300
+        occ |= bit;
+    }
+    o.reward = 0; o.terminal = 0; o.winners = 0;
+    if (s.winner1) {                                                 // :302-308 (winner persists in the state)
+        o.reward = (s.winner1 - 1 == s.mover) ? 1 : -1;
+        o.winners = 1 << (s.winner1 - 1);
+        o.terminal = 1;
+    }
+    if (occ == prm.cellmask) o.terminal = 1;                         // :310-311 draw / full board
+    o.valid_after = ~occ & prm.cellmask;
+    s.mover = (s.mover + 1 == prm.n) ? 0 : s.mover + 1;              // :313
+    s.ep_len += 1;
+}
+
+// result record, 4 bytes: int8 reward | u8 flags (1 terminal, 2 invalid action, 4 placed) | u8 winners mask |
+// u8 ranking bits (bit p = rank of player p: winners 0, everybody else 1 -- BaseEnvironment.py:173-195)
+__device__ __forceinline__ uint32_t ttt_pack_result(const TTTOut &o, const TTTParams &prm) {
+    uint32_t rank = ((1u << prm.n) - 1u) & ~(uint32_t)o.winners;
+    return ((uint32_t)o.reward & 0xffu) | (uint32_t)(o.terminal | o.error << 1 | o.placed << 2) << 8 |
+           (uint32_t)o.winners << 16 | rank << 24;
+}
+
+__device__ __forceinline__ void ttt_stats(const BlockStats &bs, bool valid, const TTTOut &o, int mover,
+                                          uint32_t ep_len, const TTTParams &prm) {
+    int t = valid && o.terminal;
+    bs.add(ST_STEPS, valid ? 1 : 0);
+    bs.add(ST_EPISODES, t);
+    bs.add(ST_EPLEN, t ? (int)ep_len : 0);
+    bs.add(ST_NOWIN, t && o.winners == 0);
+    bs.add(ST_ERRORS, valid ? o.error : 0);
+    bs.add(ST_NVALID, valid ? o.nvalid : 0);
+    bs.add(ST_REWARD, valid ? (mover + 1) * o.reward : 0);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        bs.add(ST_WINS + p, t ? (o.winners >> p & 1) : 0);
+        bs.add(ST_RANK + p, (t && p < prm.n) ? (~o.winners >> p & 1) : 0);
+    }
+}
+
+__device__ __forceinline__ void ttt_zero_out(TTTOut &o) {
+    o.reward = o.terminal = o.error = o.placed = o.winners = o.nvalid = 0; o.valid_after = 0;
+}
+
+__global__ void __launch_bounds__(256)
+ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int8_t *__restrict__ actions,
+                uint32_t *__restrict__ result, uint32_t *__restrict__ valid_after, crl_u64 *stats, long long B,
+                TTTParams prm, int flags) {
+    __shared__ int sm_stat[CRL_NSTAT];
+    BlockStats bs{sm_stat};
+    if (stats) bs.init();
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = e < B;
+    TTTOut o;
+    ttt_zero_out(o);
+    int mover = 0;
+    uint32_t ep_len = 0;
+    if (valid) {
+        TTTEnv s;
+        ttt_decode(s, ld_stream(in + e));
+        if ((flags & CRL_FLAG_AUTO_RESET) && ttt_is_terminal(s, prm)) ttt_new_state(s);
+        mover = s.mover;
+        ttt_step_env(s, (int)actions[e], prm, o);
+        ep_len = s.ep_len;
+        st_stream(out + e, ttt_encode(s));
+        result[e] = ttt_pack_result(o, prm);
+        if (valid_after) valid_after[e] = o.valid_after;
+    }
+    if (stats) {
+        ttt_stats(bs, valid, o, mover, ep_len, prm);
+        bs.flush(stats);
+    }
+}
+
+// k-th (0-based) set bit of a mask
+__device__ __forceinline__ int ttt_kth_bit(uint32_t mask, int k) {
+    for (int i = 0; i < k; i++) mask &= mask - 1;
+    return __ffs((int)mask) - 1;
+}
+
+// uniform random policy: the (r0 % n_empty)-th empty cell in C order, pass (-1) if the board is full
+__device__ __forceinline__ int ttt_random_action(const TTTEnv &s, const TTTParams &prm, uint32_t r0) {
+    uint32_t empty = ~(s.m[0] | s.m[1] | s.m[2] | s.m[3]) & prm.cellmask;
+    int n = __popc(empty);
+    return n ? ttt_kth_bit(empty, (int)(r0 % (uint32_t)n)) : -1;
+}
+
+__global__ void ttt_policy_random_kernel(const uint4 *__restrict__ st, int8_t *__restrict__ actions, long long B,
+                                         TTTParams prm, int flags, crl_u64 seed, crl_u64 first_env, uint32_t step) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B) return;
+    TTTEnv s;
+    ttt_decode(s, st[e]);
+    if ((flags & CRL_FLAG_AUTO_RESET) && ttt_is_terminal(s, prm)) ttt_new_state(s);
+    uint4 r = env_words(seed, first_env + (crl_u64)e, step, CRL_TAG_TTT);
+    actions[e] = (int8_t)ttt_random_action(s, prm, r.x);
+}
+
+__global__ void __launch_bounds__(256)
+ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl_u64 *stats, long long B,
+                   TTTParams prm, crl_u64 seed, crl_u64 first_env, uint32_t step0, int K) {
+    __shared__ int sm_stat[CRL_NSTAT];
+    BlockStats bs{sm_stat};
+    if (stats) bs.init();
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = e < B;
+    TTTEnv s;
+    TTTOut o;
+    ttt_zero_out(o);
+    ttt_new_state(s);
+    if (valid) ttt_decode(s, state[e]);
+    for (int k = 0; k < K; k++) {
+        int mover = 0;
+        if (valid) {
+            if (ttt_is_terminal(s, prm)) ttt_new_state(s);
+            uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TTT);
+            mover = s.mover;
+            ttt_step_env(s, ttt_random_action(s, prm, r.x), prm, o);
+        }
+        if (stats) ttt_stats(bs, valid, o, mover, s.ep_len, prm);
+    }
+    if (valid) {
+        state[e] = ttt_encode(s);
+        if (result) result[e] = ttt_pack_result(o, prm);
+    }
+    if (stats) bs.flush(stats);
+}
+
+__global__ void ttt_reset_kernel(uint4 *__restrict__ state, const uint8_t *__restrict__ mask, long long B) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B || (mask && !mask[e])) return;
+    state[e] = make_uint4(0, 0, 0, 0);
+}
+
+// valid_actions (tictactoe_2p_env.py:317-348): bit c set = cell c (C order) is empty; 0 <=> ['']
+__global__ void ttt_valid_kernel(const uint4 *__restrict__ st, uint32_t *__restrict__ mask, long long B, TTTParams prm) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B) return;
+    uint4 v = st[e];
+    mask[e] = ~(v.x | v.y | v.z | v.w) & prm.cellmask;
+}
+
+// state_to_observation (2p :382-407): one thread per cell.  player < 0: absolute.  mod = 2 (2p) or 3 (3p AND 4p,
+// tictactoe_4p_env.py:50).  board int8[B][cells] (-1 empty); winner int8[B] (-1 None); mover int8[B].
+__global__ void ttt_observe_kernel(const uint4 *__restrict__ st, long long B, TTTParams prm, int player,
+                                   int8_t *__restrict__ board, int8_t *__restrict__ winner, int8_t *__restrict__ mover) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * prm.cells) return;
+    long long e = idx / prm.cells;
+    int c = (int)(idx - e * prm.cells);
+    TTTEnv s;
+    ttt_decode(s, st[e]);
+    int v = -1;
+#pragma unroll
+    for (int p = 0; p < 4; p++) v = (s.m[p] >> c & 1) ? p : v;
+    if (v >= 0 && player >= 0) {
+        int mod = prm.n == 2 ? 2 : 3;
+        v = (((v - player) % mod) + mod) % mod;
+    }
+    board[idx] = (int8_t)v;
+    if (c == 0) {
+        if (winner) winner[e] = (int8_t)(s.winner1 - 1);
+        if (mover) mover[e] = (int8_t)s.mover;
+    }
+}
+
+__global__ void ttt_pack_kernel(uint4 *__restrict__ st, long long B, TTTParams prm, const int8_t *__restrict__ board,
+                                const int8_t *__restrict__ winner, const int8_t *__restrict__ mover) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B) return;
+    TTTEnv s;
+    ttt_new_state(s);
+    for (int c = 0; c < prm.cells; c++) {
+        int v = board[e * prm.cells + c];
+#pragma unroll
+        for (int p = 0; p < 4; p++) s.m[p] |= (v == p) ? (1u << c) : 0u;
+    }
+    s.winner1 = winner[e] + 1;
+    s.mover = mover[e];
+    st[e] = ttt_encode(s);
+}

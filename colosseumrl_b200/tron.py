@@ -84,6 +84,12 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         """TronGridEnvironment.next_state (:265-323).  actions: int8 [B, 4] (0 forward, 1 right, -1 left; entries of
         dead players ignored).  `players` is accepted for signature parity and ignored (dense action tensor).
         Returns (new_state, new_players mask, rewards int8 [B, P], terminal uint8 [B], winners mask uint8 [B])."""
+        new = self.step_(state, actions, out)
+        r = new.result
+        return new, r[:, 5], r[:, :self.num_players].view(torch.int8), r[:, 4], r[:, 6]
+
+    def step_(self, state: TronBatchState, actions, out: Optional[TronBatchState] = None) -> TronBatchState:
+        """The bare crl_tron_step launch (out may be `state` itself: in place).  Outputs are in new.result."""
         actions = self._dev(actions, torch.int8)
         if actions.shape != (self.batch, 4):
             raise ValueError("actions must have shape [B, 4]")
@@ -93,8 +99,7 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         self._check(self._lib.crl_tron_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
                                             new.result.data_ptr(), self.stats.data_ptr(), self.batch, self.N,
                                             self.num_players, self.flags, self._stream))
-        r = new.result
-        return new, r[:, 5], r[:, :self.num_players].view(torch.int8), r[:, 4], r[:, 6]
+        return new
 
     def valid_actions(self, state, player):
         """Always ['forward', 'right', 'left'] (:325-341): uint8 [B, 3] of ones."""

@@ -87,6 +87,71 @@ int crl_tron_observe(const void *state, int player, int8_t *board, int32_t *head
 int crl_tron_pack(void *state, const int8_t *board, const int32_t *heads, const int32_t *directions,
                   const int32_t *deaths, int64_t B, int N, int P, crl_stream_t stream);
 
+/* ------------------------------------------------------------------------------------ Tic Tac Toe
+ * n = 2 (3x3), 3 (3x5), 4 (3x3x3).  Packed state: 16 bytes per environment, uint4[B] (csrc/ttt.cuh).
+ * actions: int8[B], C-order flat cell index, negative = '' (pass).
+ * result:  4 bytes per environment: int8 reward (mover's) | u8 flags (1 terminal, 2 invalid action, 4 placed) |
+ *          u8 winners mask | u8 ranking bits (bit p = rank of p: winners 0, others 1).                      */
+int crl_ttt_cells(int n);                                                     /* HOST: 9 / 15 / 27 */
+/* HOST: the winning lines as cell masks (cross-check of WINNING_SHAPES, tictactoe_4p_env.py:19-38); returns count */
+int crl_ttt_lines(int n, uint32_t *line_masks_or_null, int capacity);
+/* new_state (tictactoe_2p_env.py:139-170) */
+int crl_ttt_reset(void *state, const uint8_t *mask_or_null, int64_t B, int n, crl_stream_t stream);
+/* next_state (2p :240-315, 3p :241-316, 4p :271-346). valid_after (uint32[B], may be NULL) receives the
+ * empty-cell mask of the NEW state (= valid_actions of the next mover). */
+int crl_ttt_step(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result,
+                 uint32_t *valid_after_or_null, int64_t *stats_or_null, int64_t B, int n, int flags,
+                 crl_stream_t stream);
+/* valid_actions (2p :317-348): bit c = cell c empty; 0 <=> [''] */
+int crl_ttt_valid_actions(const void *state, uint32_t *mask, int64_t B, int n, crl_stream_t stream);
+/* uniform random policy: the (philox(env, step, tag 3)[0] % n_empty)-th empty cell, -1 if none.  With
+ * CRL_FLAG_AUTO_RESET a finished game is treated as the fresh board the step will reset it to. */
+int crl_ttt_policy_random(const void *state, int8_t *actions, uint64_t seed, uint64_t first_env, uint32_t step,
+                          int64_t B, int n, int flags, crl_stream_t stream);
+int crl_ttt_rollout(void *state, uint8_t *result_or_null, int64_t *stats_or_null, uint64_t seed, uint64_t first_env,
+                    uint32_t step0, int K, int64_t B, int n, crl_stream_t stream);
+/* state_to_observation (2p :382-407; 4p relabels with % 3, tictactoe_4p_env.py:50). player < 0: absolute.
+ * board int8[B][cells] (-1 empty); winner int8[B] (-1 None) and mover int8[B] may be NULL. */
+int crl_ttt_observe(const void *state, int player, int8_t *board, int8_t *winner_or_null, int8_t *mover_or_null,
+                    int64_t B, int n, crl_stream_t stream);
+int crl_ttt_pack(void *state, const int8_t *board, const int8_t *winner, const int8_t *mover, int64_t B, int n,
+                 crl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ Blokus
+ * 4 players, 20x20.  Packed state: 352 bytes per game, AoS uint4[B][22] (csrc/blokus.cuh).
+ * Action id = ((piece*400 + y*20 + x)*8 + orientation)*5 + shift  for the reference's action string
+ * "{piece};({x}, {y});{orientation}{shift}" (BlokusEnvironment.py:55-106; piece in PIECE_TYPES order, board.py:24-44;
+ * orientation in ORIENTATIONS order, board.py:47); -1 = '' (pass).
+ * result: 8 bytes per game: int8 reward (mover's) | u8 flags (1 terminal, 2 illegal action, 4 placed) |
+ *         u8 winners mask | u8 ranking bits (bit p = rank of p: winners 0, others 1) | u8 next mover | 3 unused.  */
+int64_t crl_blokus_state_bytes(int64_t B);
+/* new_state (BlokusEnvironment.py:248-289) */
+int crl_blokus_reset(void *state, const uint8_t *mask_or_null, int64_t B, crl_stream_t stream);
+/* valid_actions (BlokusEnvironment.py:453-500 -> board.py:170-193 -> computation.py:145-180) for `player`
+ * (player < 0: each game's current mover).  counts int32[B] receives the full list length; action_ids
+ * int32[B][capacity] the ids in the reference's order (truncated at capacity; counts[g] > capacity signals it).
+ * counts[g] == 0 <=> [''].  With CRL_FLAG_AUTO_RESET a finished game is treated as the fresh game the step will
+ * reset it to.  stats (optional): CRL_ST_NVALID += counts. */
+int crl_blokus_legal(const void *state, int player, int32_t *counts, int32_t *action_ids, int32_t capacity,
+                     int64_t *stats_or_null, int64_t B, int flags, crl_stream_t stream);
+/* next_state (BlokusEnvironment.py:357-451): apply (board.py:87-98, ai.py:44-54), the lagged terminal test
+ * (:424: old board, old round, new inventories), winners / reward (:425-440), round / mover advance (:446-449).
+ * Unlike the reference (which applies any string blindly) an id that is not in the mover's valid list sets the
+ * illegal-action flag and is applied as a pass. */
+int crl_blokus_step(const void *state_in, void *state_out, const int32_t *actions, uint8_t *result,
+                    int64_t *stats_or_null, int64_t B, int flags, crl_stream_t stream);
+/* uniform random policy over a generated list: ids[g][philox(env, step, tag 2)[0] % counts[g]], -1 if empty */
+int crl_blokus_policy_random(const int32_t *counts, const int32_t *action_ids, int32_t capacity, int32_t *actions,
+                             uint64_t seed, uint64_t first_env, uint32_t step, int64_t B, crl_stream_t stream);
+/* state_to_observation (BlokusEnvironment.py:721-768).  player >= 0: board int8[B][20][20] of relative ids (-1
+ * empty) rotated by rot90(k=-player), pieces u8[B][4][21] by relative id, score int32[B][4] rolled by -player.
+ * player < 0: absolute unpack (board 0 empty / 1..4 colour).  meta int32[B][4] (may be NULL) = round, mover,
+ * terminal, episode steps. */
+int crl_blokus_observe(const void *state, int player, int8_t *board, uint8_t *pieces, int32_t *score,
+                       int32_t *meta_or_null, int64_t B, crl_stream_t stream);
+int crl_blokus_pack(void *state, const int8_t *board, const uint8_t *pieces, const int32_t *score, const int32_t *meta,
+                    int64_t B, crl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,190 @@
+"""Blokus parity cases against the C ABI (both backends)."""
+import os
+
+import numpy as np
+
+from oracle import oracle as orc
+from colosseumrl_b200 import philox
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def unpack_result(res):
+    res = np.asarray(res).view(np.uint8).reshape(-1, 8)
+    return dict(reward=res[:, 0].view(np.int8).astype(np.int64), terminal=(res[:, 1] & 1).astype(bool),
+                error=(res[:, 1] >> 1 & 1).astype(bool), placed=(res[:, 1] >> 2 & 1).astype(bool),
+                winners=res[:, 2].astype(np.int64), ranking=res[:, 3].astype(np.int64), next_mover=res[:, 4].astype(np.int64))
+
+
+def blk_pack(be, board, inv, scores, rounds, movers, terminal=None, ep_len=None):
+    B = board.shape[0]
+    meta = np.zeros((B, 4), np.int32)
+    meta[:, 0], meta[:, 1] = rounds, movers
+    if terminal is not None:
+        meta[:, 2] = terminal
+    if ep_len is not None:
+        meta[:, 3] = ep_len
+    st = be.zeros((B, 22, 4), np.int32)
+    args = [be.upload(np.ascontiguousarray(board, np.int8)), be.upload(np.ascontiguousarray(inv, np.uint8)),
+            be.upload(np.ascontiguousarray(scores, np.int32)), be.upload(meta)]
+    be.check(be.lib.crl_blokus_pack(be.ptr(st), *[be.ptr(a) for a in args], B, be.stream))
+    return st
+
+
+def blk_unpack(be, st, player=-1):
+    B = st.shape[0]
+    board, pieces = be.zeros((B, 20, 20), np.int8), be.zeros((B, 4, 21), np.uint8)
+    score, meta = be.zeros((B, 4), np.int32), be.zeros((B, 4), np.int32)
+    be.check(be.lib.crl_blokus_observe(be.ptr(st), player, be.ptr(board), be.ptr(pieces), be.ptr(score), be.ptr(meta), B, be.stream))
+    return tuple(be.download(x) for x in (board, pieces, score, meta))
+
+
+def blk_legal(be, st, player=-1, cap=2048, flags=0, stats=None):
+    B = st.shape[0]
+    counts, ids = be.zeros((B,), np.int32), be.zeros((B, cap), np.int32)
+    be.check(be.lib.crl_blokus_legal(be.ptr(st), player, be.ptr(counts), be.ptr(ids), cap, be.ptr(stats), B, flags, be.stream))
+    return be.download(counts), be.download(ids)
+
+
+def blk_step(be, st, actions, flags=0, stats=None):
+    B = st.shape[0]
+    a = be.upload(np.ascontiguousarray(actions, np.int32))
+    out, res = be.zeros((B, 22, 4), np.int32), be.zeros((B, 8), np.uint8)
+    be.check(be.lib.crl_blokus_step(be.ptr(st), be.ptr(out), be.ptr(a), be.ptr(res), be.ptr(stats), B, flags, be.stream))
+    return out, unpack_result(be.download(res))
+
+
+def _golden_prev(g):
+    """State before each recorded step."""
+    T = len(g["t"])
+    first = g["t"] == 0
+    board = np.where(first[:, None, None], np.int8(0), np.concatenate([np.zeros((1, 20, 20), np.int8), g["board"][:-1]], 0))
+    inv = np.where(first[:, None, None], np.uint8(1), np.concatenate([np.ones((1, 4, 21), np.uint8), g["inventory"][:-1]], 0))
+    scores = np.where(first[:, None], 0, np.concatenate([np.zeros((1, 4), np.int64), g["scores"][:-1]], 0))
+    rounds = np.where(first, 0, np.concatenate([[0], g["round"][:-1]]))
+    return board, inv, scores, rounds
+
+
+def case_golden_games(be):
+    """Every recorded transition of the reference's random games: valid_actions list (ordered), next_state outputs,
+    observations."""
+    g = np.load(os.path.join(GOLDEN, "blokus_games.npz"))
+    T = len(g["t"])
+    board, inv, scores, rounds = _golden_prev(g)
+    st = blk_pack(be, board, inv, scores, rounds, g["mover"])
+    counts, ids = blk_legal(be, st, cap=2048)
+    assert (counts == g["n_valid"]).all()
+    for i in range(T):
+        exp = g["valid_flat"][g["valid_off"][i]:g["valid_off"][i + 1]]
+        assert (ids[i, :len(exp)] == exp).all(), i
+    # explicit player argument == mover
+    for p in range(4):
+        sel = np.flatnonzero(g["mover"] == p)[:40]
+        c2, i2 = blk_legal(be, blk_pack(be, board[sel], inv[sel], scores[sel], rounds[sel], (g["mover"][sel] + 1) % 4), player=p)
+        assert (c2 == counts[sel]).all() and (i2 == ids[sel]).all()
+    out, r = blk_step(be, st, g["action"])
+    b2, p2, s2, m2 = blk_unpack(be, out)
+    assert (b2 == g["board"]).all() and (p2 == g["inventory"]).all() and (s2 == g["scores"]).all()
+    assert (m2[:, 0] == g["round"]).all() and (m2[:, 1] == g["next_mover"]).all() and (m2[:, 2] == g["terminal"]).all()
+    assert (r["reward"] == g["reward"]).all() and (r["terminal"] == g["terminal"]).all()
+    assert (r["winners"] == g["winners"]).all() and (r["next_mover"] == g["next_mover"]).all()
+    assert not r["error"].any() and (r["placed"] == (g["action"] >= 0)).all()
+    assert (r["ranking"][r["terminal"]] == (0xf & ~r["winners"][r["terminal"]])).all()
+    # observations
+    idx = g["obs_idx"]
+    sub = blk_pack(be, g["board"][idx], g["inventory"][idx], g["scores"][idx], g["round"][idx], g["next_mover"][idx])
+    for p in range(4):
+        m = g["obs_player"] == p
+        sp = blk_pack(be, g["board"][idx[m]], g["inventory"][idx[m]], g["scores"][idx[m]], g["round"][idx[m]], g["next_mover"][idx[m]])
+        ob, op, osc, _ = blk_unpack(be, sp, player=p)
+        assert (ob == g["obs_board"][m]).all(), p
+        assert (op == g["obs_pieces"][m]).all() and (osc == g["obs_score"][m]).all()
+
+
+def case_illegal_actions(be):
+    """Ids outside the mover's valid list are flagged and applied as a pass (engine contract)."""
+    g = np.load(os.path.join(GOLDEN, "blokus_games.npz"))
+    board, inv, scores, rounds = _golden_prev(g)
+    sel = np.arange(0, len(g["t"]), 3)
+    st = blk_pack(be, board[sel], inv[sel], scores[sel], rounds[sel], g["mover"][sel])
+    counts, ids = blk_legal(be, st)
+    rng = np.random.RandomState(1)
+    acts = np.zeros(len(sel), np.int32)
+    legal = np.zeros(len(sel), bool)
+    for i in range(len(sel)):
+        valid = set(ids[i, :counts[i]].tolist())
+        kind = i % 4
+        if kind == 0:
+            a = int(rng.randint(0, 21 * 16000))                      # arbitrary id
+        elif kind == 1 and counts[i]:
+            a = int(ids[i, rng.randint(counts[i])]) ^ 1              # neighbour of a legal id
+        elif kind == 2:
+            a = int(rng.randint(21 * 16000, 2 ** 30))                # piece index out of range
+        else:
+            a = int(ids[i, rng.randint(counts[i])]) if counts[i] else -1
+        acts[i] = a
+        legal[i] = a in valid or a < 0
+    out, r = blk_step(be, st, acts)
+    assert (r["error"] == ~legal).all()
+    # an illegal action must behave exactly like a pass
+    passes = np.where(legal, acts, -1)
+    out2, r2 = blk_step(be, st, passes)
+    assert (be.download(out) == be.download(out2)).all()
+    for k in ("reward", "terminal", "winners", "next_mover"):
+        assert (r[k] == r2[k]).all()
+    # and legal ones match the oracle
+    for i in np.flatnonzero(legal)[:60]:
+        j = sel[i]
+        ost = (board[j].astype(np.int64), int(rounds[j]), inv[j], scores[j])
+        nst, nxt, rew, term, win = orc.blokus_next_state(ost, int(g["mover"][j]), int(acts[i]))
+        assert rew == r["reward"][i] and term == r["terminal"][i] and (win if term else 0) == r["winners"][i]
+
+
+def case_rollout_vs_oracle(be, B=24, K=80, seed=3, env0=500, cap=2048):
+    """legal + policy + step with auto-reset and fused statistics == the oracle's rollout."""
+    ob = orc.BlokusBatch(B)
+    ob.rollout(seed, env0, 0, K, fresh=True)
+    st, st2 = be.zeros((B, 22, 4), np.int32), be.zeros((B, 22, 4), np.int32)
+    stats = be.zeros((32,), np.int64)
+    counts, ids = be.zeros((B,), np.int32), be.zeros((B, cap), np.int32)
+    act, res = be.zeros((B,), np.int32), be.zeros((B, 8), np.uint8)
+    be.check(be.lib.crl_blokus_reset(be.ptr(st), None, B, be.stream))
+    cur, nxt = st, st2
+    for t in range(K):
+        be.check(be.lib.crl_blokus_legal(be.ptr(cur), -1, be.ptr(counts), be.ptr(ids), cap, be.ptr(stats), B, 1, be.stream))
+        be.check(be.lib.crl_blokus_policy_random(be.ptr(counts), be.ptr(ids), cap, be.ptr(act), seed, env0, t, B, be.stream))
+        be.check(be.lib.crl_blokus_step(be.ptr(cur), be.ptr(nxt), be.ptr(act), be.ptr(res), be.ptr(stats), B, 1, be.stream))
+        cur, nxt = nxt, cur
+    board, pieces, score, meta = blk_unpack(be, cur)
+    assert (board == ob.board).all() and (pieces == ob.inventory).all() and (score == ob.scores).all()
+    assert (meta[:, 0] == ob.round_count).all() and (meta[:, 1] == ob.mover).all()
+    assert (meta[:, 2] == ob.terminal).all() and (meta[:, 3] == ob.ep_len).all()
+    s = be.download(stats)
+    assert (s == ob.stats).all(), (s, ob.stats)
+    assert int(be.download(counts).max()) <= cap
+
+
+def case_reset_and_capacity(be):
+    B = 9
+    st = be.zeros((B, 22, 4), np.int32)
+    be.check(be.lib.crl_blokus_reset(be.ptr(st), None, B, be.stream))
+    board, pieces, score, meta = blk_unpack(be, st)
+    assert (board == 0).all() and (pieces == 1).all() and (score == 0).all() and (meta == 0).all()
+    for p in range(4):
+        counts, ids = blk_legal(be, st, player=p)
+        assert (counts == 116).all()                                   # 116 first moves for every seat
+        exp = orc.blokus_valid_moves(orc.blokus_new_state(), p)
+        assert (ids[0, :116] == exp).all()
+    # capacity smaller than the list: count is still the full length, the prefix is written
+    counts, ids = blk_legal(be, st, player=0, cap=50)
+    assert (counts == 116).all() and (ids[3] == orc.blokus_valid_moves(orc.blokus_new_state(), 0)[:50]).all()
+    # masked reset
+    out, _ = blk_step(be, st, np.full(B, orc.blokus_encode_action(20, 0, 0, 2, 0), np.int32))
+    mask = (np.arange(B) % 2).astype(np.uint8)
+    m = be.upload(mask)
+    before = be.download(out)
+    be.check(be.lib.crl_blokus_reset(be.ptr(out), be.ptr(m), B, be.stream))
+    after = be.download(out)
+    fresh = be.download(st)
+    assert (after[mask == 1] == fresh[mask == 1]).all() and (after[mask == 0] == before[mask == 0]).all()
+    assert be.lib.crl_blokus_legal(be.ptr(st), 4, be.ptr(st), be.ptr(st), 10, None, B, 0, be.stream) == 1

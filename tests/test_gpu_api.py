@@ -1,0 +1,108 @@
+"""GPU tests of the drop-in Python surface (Batched*Environment: the BaseEnvironment method names) vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from colosseumrl_b200 import philox
+
+pytestmark = pytest.mark.gpu
+
+
+def test_registry_and_surface():
+    from colosseumrl_b200.config import get_environment, available_environments
+    assert set(available_environments()) == {"blokus", "tron", "tictactoe", "tictactoe_3p", "tictactoe_4p"}
+    env = get_environment("tron")("9;4", batch=8)
+    assert env.min_players == env.max_players == 4 and env.observation_shape["board"] == (9, 9)
+    assert env.observation_names() == ["board", "heads", "directions", "deaths"]
+    for name in ("new_state", "next_state", "valid_actions", "is_valid_action", "is_terminal", "compute_ranking",
+                 "state_to_observation", "serialize_state", "deserialize_state"):
+        assert hasattr(env, name)
+    with pytest.raises(Exception):
+        get_environment("tron")("25;4", batch=8)          # unsupported board size fails loudly
+
+
+def test_tron_api_episode():
+    from colosseumrl_b200.tron import BatchedTronGridEnvironment
+    B, N, P, seed = 257, 9, 4, 11
+    env = BatchedTronGridEnvironment("9;4", batch=B, seed=seed)
+    state, players = env.new_state()
+    assert (players.cpu().numpy() == 15).all()
+    ost = [orc.tron_new_state(N, P) for _ in range(B)]
+    for t in range(12):
+        r = philox.env_step_words(seed, np.arange(B), t, philox.TAG_TRON)
+        acts = np.array([0, 1, -1], np.int8)[(r % 3).astype(np.int64)]
+        assert (env.random_actions(t).cpu().numpy() == acts).all()
+        state, players, rewards, terminal, winners = env.next_state(state, players, torch.from_numpy(acts))   # host tensor in
+        rk = env.compute_ranking(state, None, winners).cpu().numpy()
+        obs = {p: env.state_to_observation(state, p) for p in (0, 3)}
+        for e in range(0, B, 16):
+            ost[e], alive, orew, oterm, owin = orc.tron_next_state(ost[e], acts[e])
+            assert alive == int(players[e]) and (orew == rewards[e].cpu().numpy()).all()
+            assert oterm == bool(terminal[e]) and owin == int(winners[e]) and bool(env.is_terminal(state)[e]) == oterm
+            assert (orc.tron_compute_ranking(ost[e]) == rk[e]).all()
+            for p in (0, 3):
+                oo = orc.tron_observation(ost[e], p)
+                for k in ("board", "heads", "directions", "deaths"):
+                    assert (oo[k] == obs[p][k][e].cpu().numpy()).all()
+    blob = env.serialize_state(state)
+    back = env.deserialize_state(blob)
+    assert (back.packed == state.packed).all()
+    st2 = env.state_from_arrays(*(env.state_to_observation(state, -1)[k] for k in ("board", "heads", "directions", "deaths")))
+    assert (st2.packed[:12] == state.packed[:12]).all()
+
+
+def test_ttt_api():
+    from colosseumrl_b200.tictactoe import BatchedTicTacToe4PlayerEnv, BatchedTicTacToe2PlayerEnv
+    B, seed = 300, 2
+    env = BatchedTicTacToe4PlayerEnv(batch=B, seed=seed, auto_reset=True)
+    state, players = env.new_state()
+    ob = orc.TTTBatch(B, 4)
+    for t in range(40):
+        acts = env.random_actions(state, t)
+        va = env.valid_actions(state)
+        assert env.is_valid_action(state, None, acts).cpu().numpy().astype(bool).tolist() == (acts.cpu().numpy() >= 0).tolist() or t > 0
+        state, players, reward, terminal, winners = env.next_state(state, players, acts)
+    ob.rollout(seed, 0, 0, 40, fresh=True)
+    board, winner, mover = env.state_arrays(state)
+    assert (board.cpu().numpy() == ob.board).all() and (winner.cpu().numpy() == ob.winner).all()
+    assert (mover.cpu().numpy() == ob.mover).all() and (env.stats.cpu().numpy() == ob.stats).all()
+    assert (env.is_terminal(state).cpu().numpy() == ob.terminal).all()
+    assert (players.cpu().numpy() == (1 << ob.mover)).all()
+    rk = env.compute_ranking(state, None, winners).cpu().numpy()
+    w = winners.cpu().numpy()
+    assert (rk == 1 - ((w[:, None] >> np.arange(4)[None]) & 1)).all()
+    e2 = BatchedTicTacToe2PlayerEnv(batch=4)
+    s2, _ = e2.new_state()
+    s2, pl, rew, term, win = e2.next_state(s2, None, torch.tensor([4, 4, -1, 8], dtype=torch.int8))
+    assert e2.state_to_observation(s2, 1)["board"].shape == (4, 3, 3)
+    assert (pl.cpu().numpy() == 2).all() and (term.cpu().numpy() == 0).all()
+
+
+def test_blokus_api():
+    from colosseumrl_b200.blokus import BatchedBlokusEnvironment, action_to_string, string_to_action
+    B, seed = 48, 6
+    env = BatchedBlokusEnvironment(batch=B, seed=seed, auto_reset=True)
+    state, players = env.new_state()
+    ob = orc.BlokusBatch(B)
+    for t in range(90):
+        valid = env.valid_actions(state)
+        acts = env.random_actions(valid, t)
+        if t == 5:
+            assert env.is_valid_action(state, -1, acts).cpu().numpy().all()
+            s = action_to_string(int(acts[0]))
+            assert string_to_action(s) == int(acts[0]) and s.count(";") == 2
+        state, players, reward, terminal, winners = env.next_state(state, players, acts)
+    ob.rollout(seed, 0, 0, 90, fresh=True)
+    obs = env.state_to_observation(state, -1)
+    assert (obs["board"].cpu().numpy() == ob.board).all() and (obs["pieces"].cpu().numpy() == ob.inventory).all()
+    assert (obs["score"].cpu().numpy() == ob.scores).all() and (obs["mover"].cpu().numpy() == ob.mover).all()
+    assert (env.is_terminal(state).cpu().numpy() == ob.terminal).all()
+    assert (env.stats.cpu().numpy() == ob.stats).all()
+    assert (env.current_rewards(state).cpu().numpy() == ob.scores).all()
+    for p in range(4):
+        o = env.state_to_observation(state, p)
+        e = 7
+        oo = orc.blokus_observation((ob.board[e], ob.round_count[e], ob.inventory[e], ob.scores[e]), p)
+        assert (o["board"][e].cpu().numpy() == oo["board"]).all() and (o["pieces"][e].cpu().numpy() == oo["pieces"]).all()
+        assert (o["score"][e].cpu().numpy() == oo["score"]).all()

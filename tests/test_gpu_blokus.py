@@ -1,0 +1,33 @@
+"""GPU parity tests (B200): Blokus through the C ABI vs the oracle / golden vectors."""
+import pytest
+
+import backends
+import cases_blokus as cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    return backends.Cuda()
+
+
+def test_reset_and_capacity(be):
+    cases.case_reset_and_capacity(be)
+
+
+def test_golden_games(be):
+    cases.case_golden_games(be)
+
+
+def test_illegal_actions(be):
+    cases.case_illegal_actions(be)
+
+
+def test_rollout_vs_oracle(be):
+    cases.case_rollout_vs_oracle(be, B=64, K=150)
+
+
+def test_rollout_vs_oracle_wide(be):
+    # many games, two+ full episodes each: end states and fused statistics bit-exact vs the oracle
+    cases.case_rollout_vs_oracle(be, B=1024, K=150, seed=0, env0=0)

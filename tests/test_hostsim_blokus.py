@@ -1,0 +1,26 @@
+"""CPU unit tests: the Blokus kernel SOURCE (csrc/blokus.cuh, warp-level code) on the SIMT emulator vs oracle / golden."""
+import pytest
+
+import backends
+import cases_blokus as cases
+
+
+@pytest.fixture(scope="module")
+def be():
+    return backends.HostSim()
+
+
+def test_reset_and_capacity(be):
+    cases.case_reset_and_capacity(be)
+
+
+def test_golden_games(be):
+    cases.case_golden_games(be)
+
+
+def test_illegal_actions(be):
+    cases.case_illegal_actions(be)
+
+
+def test_rollout_vs_oracle(be):
+    cases.case_rollout_vs_oracle(be, B=8, K=76)
