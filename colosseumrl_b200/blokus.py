@@ -75,7 +75,7 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         return BlokusBatchState(packed), torch.ones((self.batch,), dtype=torch.uint8, device=self.device)
 
     def valid_actions(self, state: BlokusBatchState, player: int = -1,
-                      out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+                      out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, count_stats: bool = True):
         """valid_actions (:453-500): (counts int32 [B], ids int32 [B, capacity]) in the reference's order;
         counts == 0 <=> [''].  player = -1: each game's current mover."""
         if out is None:
@@ -83,12 +83,13 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
                    torch.empty((self.batch, self.capacity), dtype=torch.int32, device=self.device))
         counts, ids = out
         self._check(self._lib.crl_blokus_legal(state.packed.data_ptr(), int(player), counts.data_ptr(), ids.data_ptr(),
-                                               ids.shape[1], self.stats.data_ptr(), self.batch, self.flags, self._stream))
+                                               ids.shape[1], self.stats.data_ptr() if count_stats else None, self.batch,
+                                               self.flags, self._stream))
         return counts, ids
 
     def is_valid_action(self, state: BlokusBatchState, player: int, action) -> torch.Tensor:
         action = self._dev(action, torch.int32)
-        counts, ids = self.valid_actions(state, player)
+        counts, ids = self.valid_actions(state, player, count_stats=False)
         slot = torch.arange(ids.shape[1], device=self.device)[None]
         return (((ids == action[:, None]) & (slot < counts[:, None])).any(dim=1) & (action >= 0)).to(torch.uint8)
 
