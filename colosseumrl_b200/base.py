@@ -131,7 +131,5 @@ class BatchedBaseEnvironment(ABC):
 
     def all_reduce_stats(self) -> torch.Tensor:
         """Sum the episode statistics over all ranks (the only collective of the engine)."""
-        out = self.stats.clone()
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM)
-        return out
+        from .sharding import all_reduce_stats
+        return all_reduce_stats(self.stats)

@@ -125,13 +125,17 @@ static int tron_starts(int N, int P, int32_t *heads, int32_t *dirs) {
 static int tron_params(int N, int P, TronParams &prm) {
     int32_t heads[4] = {0, 0, 0, 0}, dirs[4] = {0, 0, 0, 0};
     if (tron_starts(N, P, heads, dirs) != CRL_OK) return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N/P%s");
-    prm.N = N; prm.P = P; prm.start_dirs = 0;
+    prm.N = N; prm.P = P;
+    TronHdr h;
     for (int p = 0; p < 4; p++) {
-        prm.start_head[p] = p < P ? (uint32_t)(heads[p] % N) | (uint32_t)(heads[p] / N) << 8 : 0;
-        prm.start_dirs |= (p < P ? (uint32_t)dirs[p] : 0u) << (2 * p);
+        h.hx[p] = p < P ? heads[p] % N : 0; h.hy[p] = p < P ? heads[p] / N : 0;
+        h.dir[p] = p < P ? dirs[p] : 0; h.death[p] = 0; h.cells[p] = p < P ? 1 : 0;
         for (int w = 0; w < TRON_WORDS; w++)
             prm.start_pl[p][w] = (p < P && (heads[p] >> 6) == w) ? 1ull << (heads[p] & 63) : 0ull;
     }
+    h.terminal = 0; h.ep_len = 0;
+    uint4 e = tron_hdr_encode(h);
+    prm.start_hdr[0] = e.x; prm.start_hdr[1] = e.y; prm.start_hdr[2] = e.z; prm.start_hdr[3] = e.w;
     return CRL_OK;
 }
 
@@ -155,7 +159,7 @@ int crl_tron_reset(void *state, const uint8_t *mask, int64_t B, int N, int P, cr
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(tron_reset_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (uint4 *)state, mask, (long long)B, prm);
+    CRL_LAUNCH(tron_reset_kernel, blocks_for(B * TRON_VEC, 256), 256, (cudaStream_t)stream, (uint4 *)state, mask, (long long)B, prm);
     return check_launch("tron_reset_kernel");
 }
 
@@ -167,7 +171,7 @@ int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, 
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(tron_step_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (const uint4 *)state_in,
+    CRL_LAUNCH(tron_step_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (const uint4 *)state_in,
                (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags);
     return check_launch("tron_step_kernel");
 }
@@ -189,7 +193,7 @@ int crl_tron_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0 || K == 0) return CRL_OK;
-    CRL_LAUNCH(tron_rollout_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (uint4 *)state, (uint2 *)result,
+    CRL_LAUNCH(tron_rollout_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (uint4 *)state, (uint2 *)result,
                (crl_u64 *)stats, (long long)B, prm, (crl_u64)seed, (crl_u64)first_env, step0, K);
     return check_launch("tron_rollout_kernel");
 }

@@ -10,29 +10,34 @@
 // HBM layout (SoA of 16-byte vectors, [13][B] uint4, 208 B per environment):
 //   vector v = 3*p + j (p = player plane 0..3, j = 0..2): 64-bit words 2j and 2j+1 of plane p's bitboard,
 //             bit (y*N + x) of the 384-bit plane is set iff player p owns cell (x, y)   (N*N <= 384, N <= 19)
-//   vector 12 = header: .x = head0 | head1 << 16, .y = head2 | head3 << 16   (head = x | y << 8)
-//                       .z = directions (2 bit each, bits 0-7) | deaths (3 bit each, bits 8-19) | terminal << 20
-//                       .w = steps taken in the current episode
-// Thread t of a warp loads vector v of environment e0 + t: every load/store instruction of a warp is one
-// contiguous, 512-byte, 128-bit-per-lane access.  One thread owns one environment (the dynamics are a
-// 4-iteration dependent chain; there is nothing to share between lanes).
+//   vector 12 = header:
+//     .x = head0 | head1 << 10 | head2 << 20                      (head = x | y << 5)
+//     .y = head3 | directions << 10 (2 bit each) | deaths << 18 (3 bit each) | terminal << 30
+//     .z = cells0 | cells1 << 9 | cells2 << 18                    (#cells owned = compute_ranking's score)
+//     .w = cells3 | episode steps << 9
+//
+// Data movement: vector v of the TILE environments of a CTA is ONE contiguous global segment (TILE*16 bytes), so
+// the whole tile travels as 13 bulk-async copies (TMA, cp.async.bulk -> SASS UBLKCP) issued by one thread into
+// shared memory and 13 back; the planes are never unpacked into registers.  Each thread owns one environment and
+// only touches the <= 4 bitboard words its players move into (dynamic word index = a shared-memory address, not
+// a register-select chain) plus the 16-byte header.  The #cells per player is carried in the header so the
+// ranking needs no popcounts.
 #pragma once
 #include "crl_common.cuh"
 #include "philox.cuh"
 
 #define TRON_VEC 13
 #define TRON_WORDS 6
+#define TRON_TILE 64          // environments (= threads) per CTA: 13 KB of shared memory, ~7 CTAs per SM at B = 65,536
 
 struct TronParams {
     int N, P;
-    uint32_t start_head[4];             // x | y << 8
-    uint32_t start_dirs;                // 2 bits per player
+    uint32_t start_hdr[4];              // header of new_state()
     uint64_t start_pl[4][TRON_WORDS];   // bitboards of new_state(): one bit per player at its spawn
 };
 
-struct TronEnv {
-    uint64_t pl[4][TRON_WORDS];
-    int hx[4], hy[4], dir[4], death[4];
+struct TronHdr {
+    int hx[4], hy[4], dir[4], death[4], cells[4];
     uint32_t terminal, ep_len;
 };
 
@@ -41,8 +46,7 @@ struct TronOut {
     int alive, winners, terminal, rank[4], cells[4];
 };
 
-// Register arrays are only ever indexed with compile-time constants (a dynamic index would demote them to
-// local memory); run-time selection is done with masks.
+// Register arrays are only ever indexed with compile-time constants; run-time selection is done with masks.
 __device__ __forceinline__ int tron_sel4(const int (&a)[4], int k) {
     int r = 0;
 #pragma unroll
@@ -50,64 +54,96 @@ __device__ __forceinline__ int tron_sel4(const int (&a)[4], int k) {
     return r;
 }
 
-__device__ __forceinline__ void tron_load(TronEnv &s, const uint4 *__restrict__ st, long long B, long long e) {
-    uint4 v[TRON_VEC];
-#pragma unroll
-    for (int i = 0; i < TRON_VEC; i++) v[i] = ld_stream(st + (long long)i * B + e);
-#pragma unroll
-    for (int p = 0; p < 4; p++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            s.pl[p][2 * j] = (uint64_t)v[3 * p + j].x | ((uint64_t)v[3 * p + j].y << 32);
-            s.pl[p][2 * j + 1] = (uint64_t)v[3 * p + j].z | ((uint64_t)v[3 * p + j].w << 32);
-        }
-    uint4 h = v[12];
-    uint32_t hd[4] = {h.x & 0xffffu, h.x >> 16, h.y & 0xffffu, h.y >> 16};
+__device__ __forceinline__ void tron_hdr_decode(TronHdr &s, uint4 h) {
+    uint32_t hd[4] = {h.x & 1023u, (h.x >> 10) & 1023u, (h.x >> 20) & 1023u, h.y & 1023u};
+    uint32_t ce[4] = {h.z & 511u, (h.z >> 9) & 511u, (h.z >> 18) & 511u, h.w & 511u};
 #pragma unroll
     for (int p = 0; p < 4; p++) {
-        s.hx[p] = hd[p] & 0xff; s.hy[p] = hd[p] >> 8;
-        s.dir[p] = (h.z >> (2 * p)) & 3;
-        s.death[p] = (h.z >> (8 + 3 * p)) & 7;
+        s.hx[p] = hd[p] & 31; s.hy[p] = hd[p] >> 5;
+        s.dir[p] = (h.y >> (10 + 2 * p)) & 3;
+        s.death[p] = (h.y >> (18 + 3 * p)) & 7;
+        s.cells[p] = (int)ce[p];
     }
-    s.terminal = (h.z >> 20) & 1;
-    s.ep_len = h.w;
+    s.terminal = (h.y >> 30) & 1;
+    s.ep_len = h.w >> 9;
 }
 
-__device__ __forceinline__ void tron_store(const TronEnv &s, uint4 *__restrict__ st, long long B, long long e) {
-#pragma unroll
-    for (int p = 0; p < 4; p++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            uint64_t a = s.pl[p][2 * j], b = s.pl[p][2 * j + 1];
-            st_stream(st + (long long)(3 * p + j) * B + e,
-                      make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32)));
-        }
-    uint32_t hd[4], z = s.terminal << 20;
+__host__ __device__ __forceinline__ uint4 tron_hdr_encode(const TronHdr &s) {
+    uint32_t hd[4], y = s.terminal << 30;
 #pragma unroll
     for (int p = 0; p < 4; p++) {
-        hd[p] = (uint32_t)s.hx[p] | ((uint32_t)s.hy[p] << 8);
-        z |= (uint32_t)s.dir[p] << (2 * p);
-        z |= (uint32_t)s.death[p] << (8 + 3 * p);
+        hd[p] = (uint32_t)s.hx[p] | ((uint32_t)s.hy[p] << 5);
+        y |= (uint32_t)s.dir[p] << (10 + 2 * p);
+        y |= (uint32_t)s.death[p] << (18 + 3 * p);
     }
-    st_stream(st + (long long)12 * B + e, make_uint4(hd[0] | hd[1] << 16, hd[2] | hd[3] << 16, z, s.ep_len));
+    return make_uint4(hd[0] | hd[1] << 10 | hd[2] << 20, hd[3] | y,
+                      (uint32_t)s.cells[0] | (uint32_t)s.cells[1] << 9 | (uint32_t)s.cells[2] << 18,
+                      (uint32_t)s.cells[3] | s.ep_len << 9);
+}
+
+// ---- the shared-memory tile ---------------------------------------------------------------------------------
+struct TronTile {
+    uint4 v[TRON_VEC][TRON_TILE];
+};
+
+// 64-bit word w of plane p of the environment owned by thread t
+__device__ __forceinline__ uint64_t *tron_word(TronTile &tile, int t, int p, int w) {
+    return reinterpret_cast<uint64_t *>(&tile.v[3 * p + (w >> 1)][t]) + (w & 1);
+}
+
+// global -> shared (n <= TRON_TILE environments starting at e0)
+__device__ __forceinline__ void tron_tile_load(TronTile &tile, uint64_t *bar, const uint4 *__restrict__ st,
+                                               long long B, long long e0, int n) {
+#ifndef CRL_HOSTSIM
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)(TRON_VEC * n * 16));
+#pragma unroll
+        for (int v = 0; v < TRON_VEC; v++) bulk_g2s(&tile.v[v][0], st + (long long)v * B + e0, (uint32_t)(n * 16), bar);
+    }
+    __syncthreads();           // barrier initialisation visible to the waiters
+    mbar_wait(bar, 0);
+#else
+    for (int v = 0; v < TRON_VEC; v++)
+        if ((int)threadIdx.x < n) tile.v[v][threadIdx.x] = st[(long long)v * B + e0 + threadIdx.x];
+    __syncthreads();
+#endif
+}
+
+// shared -> global
+__device__ __forceinline__ void tron_tile_store(TronTile &tile, uint4 *__restrict__ st, long long B, long long e0, int n) {
+#ifndef CRL_HOSTSIM
+    fence_async_smem();        // generic-proxy writes to the tile -> visible to the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int v = 0; v < TRON_VEC; v++) bulk_s2g(st + (long long)v * B + e0, &tile.v[v][0], (uint32_t)(n * 16));
+        bulk_commit_wait_read();   // the tile may be released once the copies have read it
+    }
+#else
+    __syncthreads();
+    for (int v = 0; v < TRON_VEC; v++)
+        if ((int)threadIdx.x < n) st[(long long)v * B + e0 + threadIdx.x] = tile.v[v][threadIdx.x];
+    __syncthreads();
+#endif
 }
 
 // new_state (TronGridEnvironment.py:228-263): empty board, p+1 written at each head (:261)
-__device__ __forceinline__ void tron_new_state(TronEnv &s, const TronParams &prm) {
+__device__ __forceinline__ void tron_new_state(TronTile &tile, int t, TronHdr &s, const TronParams &prm) {
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
+    for (int p = 0; p < 4; p++)
 #pragma unroll
-        for (int w = 0; w < TRON_WORDS; w++) s.pl[p][w] = prm.start_pl[p][w];
-        s.hx[p] = prm.start_head[p] & 0xff; s.hy[p] = prm.start_head[p] >> 8;
-        s.dir[p] = (prm.start_dirs >> (2 * p)) & 3;
-        s.death[p] = 0;
-    }
-    s.terminal = 0; s.ep_len = 0;
+        for (int j = 0; j < 3; j++) {
+            uint64_t a = prm.start_pl[p][2 * j], b = prm.start_pl[p][2 * j + 1];
+            tile.v[3 * p + j][t] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+        }
+    tron_hdr_decode(s, make_uint4(prm.start_hdr[0], prm.start_hdr[1], prm.start_hdr[2], prm.start_hdr[3]));
 }
 
 // One env-step: CyTronGrid.pyx:15-62 (players strictly in index order against the already-updated board),
 // then TronGridEnvironment.py:309-321 and the ranking of :483-508.
-__device__ __forceinline__ void tron_step_env(TronEnv &s, const int (&act)[4], const TronParams &prm, TronOut &o) {
+__device__ __forceinline__ void tron_step_env(TronTile &tile, int t, TronHdr &s, const int (&act)[4],
+                                              const TronParams &prm, TronOut &o) {
     const int N = prm.N, P = prm.P;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -119,27 +155,20 @@ __device__ __forceinline__ void tron_step_env(TronEnv &s, const int (&act)[4], c
             if ((unsigned)x >= (unsigned)N || (unsigned)y >= (unsigned)N) {
                 s.death[i] = i + 1;                                      // pyx:47-48
             } else {
-                int c = y * N + x, w = c >> 6;
-                uint64_t bit = 1ull << (c & 63), m[TRON_WORDS];
-#pragma unroll
-                for (int ww = 0; ww < TRON_WORDS; ww++) m[ww] = (ww == w) ? bit : 0ull;
+                const int c = y * N + x, w = c >> 6;
+                const uint64_t bit = 1ull << (c & 63);
                 int owner = 0;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    uint64_t hit = 0;
-#pragma unroll
-                    for (int ww = 0; ww < TRON_WORDS; ww++) hit |= s.pl[q][ww] & m[ww];
-                    owner = hit ? q + 1 : owner;
-                }
+                for (int q = 0; q < 4; q++) owner = (*tron_word(tile, t, q, w) & bit) ? q + 1 : owner;
                 if (owner) {
                     s.death[i] = owner;                                  // pyx:51-53
 #pragma unroll
                     for (int q = 0; q < 4; q++)                          // pyx:56-57 (no liveness check: T3)
                         if (owner == q + 1 && s.hx[q] == x && s.hy[q] == y) s.death[q] = i + 1;
                 } else {
-#pragma unroll
-                    for (int ww = 0; ww < TRON_WORDS; ww++) s.pl[i][ww] |= m[ww];   // pyx:60-62
+                    *tron_word(tile, t, i, w) |= bit;                    // pyx:60-62
                     s.hx[i] = x; s.hy[i] = y;
+                    s.cells[i] += 1;
                 }
             }
         }
@@ -156,15 +185,10 @@ __device__ __forceinline__ void tron_step_env(TronEnv &s, const int (&act)[4], c
         if (o.winners >> p & 1) r += 9;                                  // py:320-321
         o.reward[p] = r;
     }
-    // ---- compute_ranking (py:483-508)
+    // ---- compute_ranking (py:483-508); score = #cells owned, carried in the header
     int score[4];
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-        int n = 0;
-#pragma unroll
-        for (int w = 0; w < TRON_WORDS; w++) n += __popcll(s.pl[p][w]);
-        score[p] = n; o.cells[p] = n;
-    }
+    for (int p = 0; p < 4; p++) { score[p] = s.cells[p]; o.cells[p] = s.cells[p]; }
     int tie = 0;  // tie_locations are evaluated up front (py:492); deaths[-1] addresses the LAST player
 #pragma unroll
     for (int p = 0; p < 4; p++) {
@@ -201,21 +225,44 @@ __device__ __forceinline__ uint2 tron_pack_result(const TronOut &o) {
     return make_uint2(a, (uint32_t)o.terminal | (uint32_t)o.alive << 8 | (uint32_t)o.winners << 16 | rk << 24);
 }
 
-__device__ __forceinline__ void tron_stats(const BlockStats &bs, bool valid, const TronOut &o, uint32_t ep_len) {
-    int t = valid && o.terminal;
-    bs.add(ST_STEPS, valid ? 1 : 0);
-    bs.add(ST_EPISODES, t);
-    bs.add(ST_EPLEN, t ? (int)ep_len : 0);
-    bs.add(ST_NOWIN, t && o.winners == 0);
+// Episode statistics of one step: 19 counters packed into 6 words so a warp needs 6 redux.sync, not 19.
+__device__ __forceinline__ void tron_stats(int *sm_stat, bool valid, const TronOut &o, uint32_t ep_len) {
+    const int t = valid && o.terminal;
     int rw = 0;
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-        bs.add(ST_WINS + p, t ? (o.winners >> p & 1) : 0);
-        bs.add(ST_SCORE + p, t ? o.cells[p] : 0);
-        bs.add(ST_RANK + p, t ? o.rank[p] : 0);
-        rw += (p + 1) * o.reward[p];
+    for (int p = 0; p < 4; p++) rw += (p + 1) * o.reward[p];
+    const int w0 = o.winners & -t, nr = t;
+    // every field is a sum of <= 32 lane values and stays inside its bit range
+    uint32_t A = (valid ? 1u : 0u) | (uint32_t)t << 8 | (uint32_t)(t && o.winners == 0) << 16 | (uint32_t)(w0 & 1) << 24;
+    uint32_t Bw = (uint32_t)(w0 >> 1 & 1) | (uint32_t)(w0 >> 2 & 1) << 8 | (uint32_t)(w0 >> 3 & 1) << 16;
+    uint32_t C = nr ? ((uint32_t)o.rank[0] | (uint32_t)o.rank[1] << 8 | (uint32_t)o.rank[2] << 16 | (uint32_t)o.rank[3] << 24) : 0u;
+    uint32_t D = (t ? ep_len : 0u) | (uint32_t)((valid ? rw : 0) + 16) << 16;          // reward sum biased by +16 per lane
+    uint32_t E = t ? ((uint32_t)o.cells[0] | (uint32_t)o.cells[1] << 16) : 0u;
+    uint32_t F = t ? ((uint32_t)o.cells[2] | (uint32_t)o.cells[3] << 16) : 0u;
+    A = __reduce_add_sync(0xffffffffu, A); Bw = __reduce_add_sync(0xffffffffu, Bw);
+    C = __reduce_add_sync(0xffffffffu, C); D = __reduce_add_sync(0xffffffffu, D);
+    E = __reduce_add_sync(0xffffffffu, E); F = __reduce_add_sync(0xffffffffu, F);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sm_stat[ST_STEPS], (int)(A & 255u));
+        if (A >> 8) {
+            atomicAdd(&sm_stat[ST_EPISODES], (int)(A >> 8 & 255u));
+            atomicAdd(&sm_stat[ST_NOWIN], (int)(A >> 16 & 255u));
+            atomicAdd(&sm_stat[ST_WINS + 0], (int)(A >> 24));
+            atomicAdd(&sm_stat[ST_WINS + 1], (int)(Bw & 255u));
+            atomicAdd(&sm_stat[ST_WINS + 2], (int)(Bw >> 8 & 255u));
+            atomicAdd(&sm_stat[ST_WINS + 3], (int)(Bw >> 16 & 255u));
+            atomicAdd(&sm_stat[ST_RANK + 0], (int)(C & 255u));
+            atomicAdd(&sm_stat[ST_RANK + 1], (int)(C >> 8 & 255u));
+            atomicAdd(&sm_stat[ST_RANK + 2], (int)(C >> 16 & 255u));
+            atomicAdd(&sm_stat[ST_RANK + 3], (int)(C >> 24));
+            atomicAdd(&sm_stat[ST_EPLEN], (int)(D & 0xffffu));
+            atomicAdd(&sm_stat[ST_SCORE + 0], (int)(E & 0xffffu));
+            atomicAdd(&sm_stat[ST_SCORE + 1], (int)(E >> 16));
+            atomicAdd(&sm_stat[ST_SCORE + 2], (int)(F & 0xffffu));
+            atomicAdd(&sm_stat[ST_SCORE + 3], (int)(F >> 16));
+        }
+        atomicAdd(&sm_stat[ST_REWARD], (int)(D >> 16) - 16 * 32);
     }
-    bs.add(ST_REWARD, valid ? rw : 0);
 }
 
 __device__ __forceinline__ void tron_zero_out(TronOut &o) {
@@ -226,68 +273,82 @@ __device__ __forceinline__ void tron_zero_out(TronOut &o) {
 
 // actions: int8[B][4] (0 forward, +1 right, -1 left  == STRING_TO_ACTION, TronGridEnvironment.py:62-67), one
 // coalesced 32-bit load per environment.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TRON_TILE)
 tron_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const uint32_t *__restrict__ actions,
                  uint2 *__restrict__ result, crl_u64 *stats, long long B, TronParams prm, int flags) {
+    __shared__ __align__(128) TronTile tile;
+    __shared__ __align__(8) uint64_t bar;
     __shared__ int sm_stat[CRL_NSTAT];
-    BlockStats bs{sm_stat};
-    if (stats) bs.init();
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = e < B;
+    const int t = threadIdx.x;
+    const long long e0 = (long long)blockIdx.x * TRON_TILE;
+    const int n = (int)min((long long)TRON_TILE, B - e0);
+    const bool valid = t < n;
+    if (stats && t < CRL_NSTAT) sm_stat[t] = 0;
+    const uint32_t a = valid ? actions[e0 + t] : 0u;       // overlaps with the tile's flight
+    tron_tile_load(tile, &bar, in, B, e0, n);
     TronOut o;
     tron_zero_out(o);
     uint32_t ep_len = 0;
     if (valid) {
-        TronEnv s;
-        tron_load(s, in, B, e);
-        uint32_t a = actions[e];
-        if ((flags & CRL_FLAG_AUTO_RESET) && s.terminal) tron_new_state(s, prm);
+        TronHdr s;
+        tron_hdr_decode(s, tile.v[12][t]);
+        if ((flags & CRL_FLAG_AUTO_RESET) && s.terminal) tron_new_state(tile, t, s, prm);
         int act[4];
 #pragma unroll
         for (int p = 0; p < 4; p++) act[p] = (int)(int8_t)(a >> (8 * p));
-        tron_step_env(s, act, prm, o);
+        tron_step_env(tile, t, s, act, prm, o);
         ep_len = s.ep_len;
-        tron_store(s, out, B, e);
-        result[e] = tron_pack_result(o);
+        tile.v[12][t] = tron_hdr_encode(s);
+        result[e0 + t] = tron_pack_result(o);
     }
+    tron_tile_store(tile, out, B, e0, n);
     if (stats) {
-        tron_stats(bs, valid, o, ep_len);
-        bs.flush(stats);
+        tron_stats(sm_stat, valid, o, ep_len);
+        __syncthreads();
+        if (t < CRL_NSTAT && sm_stat[t] != 0) atomicAdd(stats + t, (crl_u64)(long long)sm_stat[t]);
     }
 }
 
-// K fused steps with the in-kernel Philox random policy (action of player p = {0,+1,-1}[r_p % 3]); the state
-// stays in registers between steps.  Benchmark / self-play helper; semantics identical to K tron_step calls
+// K fused steps with the in-kernel Philox random policy (action of player p = {0,+1,-1}[r_p % 3]); the tile
+// stays in shared memory between steps.  Benchmark / self-play helper; semantics identical to K tron_step calls
 // with CRL_FLAG_AUTO_RESET.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TRON_TILE)
 tron_rollout_kernel(uint4 *__restrict__ state, uint2 *__restrict__ result, crl_u64 *stats, long long B,
                     TronParams prm, crl_u64 seed, crl_u64 first_env, uint32_t step0, int K) {
+    __shared__ __align__(128) TronTile tile;
+    __shared__ __align__(8) uint64_t bar;
     __shared__ int sm_stat[CRL_NSTAT];
-    BlockStats bs{sm_stat};
-    if (stats) bs.init();
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = e < B;
-    TronEnv s;
+    const int t = threadIdx.x;
+    const long long e0 = (long long)blockIdx.x * TRON_TILE;
+    const int n = (int)min((long long)TRON_TILE, B - e0);
+    const bool valid = t < n;
+    if (stats && t < CRL_NSTAT) sm_stat[t] = 0;
+    tron_tile_load(tile, &bar, state, B, e0, n);
+    TronHdr s;
     TronOut o;
     tron_zero_out(o);
-    if (valid) tron_load(s, state, B, e); else tron_new_state(s, prm);
+    tron_hdr_decode(s, valid ? tile.v[12][t] : make_uint4(0, 0, 0, 0));
     for (int k = 0; k < K; k++) {
         if (valid) {
-            if (s.terminal) tron_new_state(s, prm);
-            uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TRON);
+            if (s.terminal) tron_new_state(tile, t, s, prm);
+            uint4 r = env_words(seed, first_env + (crl_u64)(e0 + t), step0 + (uint32_t)k, CRL_TAG_TRON);
             uint32_t rr[4] = {r.x, r.y, r.z, r.w};
             int act[4];
 #pragma unroll
             for (int p = 0; p < 4; p++) { int m = (int)(rr[p] % 3u); act[p] = (m == 2) ? -1 : m; }
-            tron_step_env(s, act, prm, o);
+            tron_step_env(tile, t, s, act, prm, o);
         }
-        if (stats) tron_stats(bs, valid, o, s.ep_len);
+        if (stats) tron_stats(sm_stat, valid, o, s.ep_len);
     }
     if (valid) {
-        tron_store(s, state, B, e);
-        if (result) result[e] = tron_pack_result(o);
+        tile.v[12][t] = tron_hdr_encode(s);
+        if (result) result[e0 + t] = tron_pack_result(o);
     }
-    if (stats) bs.flush(stats);
+    tron_tile_store(tile, state, B, e0, n);
+    if (stats) {
+        __syncthreads();
+        if (t < CRL_NSTAT && sm_stat[t] != 0) atomicAdd(stats + t, (crl_u64)(long long)sm_stat[t]);
+    }
 }
 
 __global__ void tron_policy_random_kernel(uint32_t *__restrict__ actions, long long B, crl_u64 seed,
@@ -301,13 +362,23 @@ __global__ void tron_policy_random_kernel(uint32_t *__restrict__ actions, long l
     actions[e] = a;
 }
 
-__global__ void __launch_bounds__(128)
-tron_reset_kernel(uint4 *__restrict__ state, const uint8_t *__restrict__ mask, long long B, TronParams prm) {
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B || (mask && !mask[e])) return;
-    TronEnv s;
-    tron_new_state(s, prm);
-    tron_store(s, state, B, e);
+// new_state for all / masked environments: one thread per (vector, environment), fully coalesced stores
+__global__ void tron_reset_kernel(uint4 *__restrict__ state, const uint8_t *__restrict__ mask, long long B, TronParams prm) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * TRON_VEC) return;
+    const int v = (int)(idx / B);
+    const long long e = idx - (long long)v * B;
+    if (mask && !mask[e]) return;
+    uint4 val = make_uint4(prm.start_hdr[0], prm.start_hdr[1], prm.start_hdr[2], prm.start_hdr[3]);
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (v == 3 * p + j) {
+                uint64_t a = prm.start_pl[p][2 * j], b = prm.start_pl[p][2 * j + 1];
+                val = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+            }
+    state[idx] = val;
 }
 
 // state_to_observation (TronGridEnvironment.py:385-405): one thread per board cell.  player < 0 => absolute
@@ -332,36 +403,41 @@ __global__ void tron_observe_kernel(const uint4 *__restrict__ st, long long B, T
     if (v > 0 && player >= 0) v = ((v - (player + 1) + P) % P) + 1;      // CyTronGrid.pyx:65-71
     board[idx] = (int8_t)v;
     if (c < P) {
-        uint4 h = st[(long long)12 * B + e];
+        TronHdr s;
+        tron_hdr_decode(s, st[(long long)12 * B + e]);
         int src = player >= 0 ? (c + player) % P : c;                    // py:392
-        uint32_t hd = (src < 2 ? h.x : h.y) >> (16 * (src & 1)) & 0xffffu;
-        if (heads) heads[e * P + c] = (int)(hd >> 8) * N + (int)(hd & 0xff);
-        if (dirs) dirs[e * P + c] = (h.z >> (2 * src)) & 3;
-        if (deaths) deaths[e * P + c] = (h.z >> (8 + 3 * src)) & 7;
-        if (terminal && c == 0) terminal[e] = (h.z >> 20) & 1;
+        if (heads) heads[e * P + c] = tron_sel4(s.hy, src) * N + tron_sel4(s.hx, src);
+        if (dirs) dirs[e * P + c] = tron_sel4(s.dir, src);
+        if (deaths) deaths[e * P + c] = tron_sel4(s.death, src);
+        if (terminal && c == 0) terminal[e] = (uint8_t)s.terminal;
     }
 }
 
-// import a reference-layout state (board int8[B][N][N], heads (y*N+x) / directions / deaths int32[B][P])
+// import a reference-layout state (board int8[B][N][N], heads (y*N+x) / directions / deaths int32[B][P]);
+// one thread per environment (import path, not performance critical)
 __global__ void tron_pack_kernel(uint4 *__restrict__ st, long long B, TronParams prm,
                                  const int8_t *__restrict__ board, const int32_t *__restrict__ heads,
                                  const int32_t *__restrict__ dirs, const int32_t *__restrict__ deaths) {
     const int N = prm.N, P = prm.P, NN = N * N;
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B) return;
-    TronEnv s;
-    tron_new_state(s, prm);
+    uint64_t pl[4][TRON_WORDS];
+    TronHdr s;
 #pragma unroll
-    for (int p = 0; p < 4; p++)
+    for (int p = 0; p < 4; p++) {
 #pragma unroll
-        for (int w = 0; w < TRON_WORDS; w++) s.pl[p][w] = 0;
+        for (int w = 0; w < TRON_WORDS; w++) pl[p][w] = 0;
+        s.hx[p] = s.hy[p] = s.dir[p] = s.death[p] = s.cells[p] = 0;
+    }
     for (int c = 0; c < NN; c++) {
         int v = board[e * NN + c];
 #pragma unroll
-        for (int p = 0; p < 4; p++)
+        for (int p = 0; p < 4; p++) {
+            s.cells[p] += (v == p + 1);
 #pragma unroll
             for (int w = 0; w < TRON_WORDS; w++)
-                s.pl[p][w] |= (v == p + 1 && w == (c >> 6)) ? (1ull << (c & 63)) : 0ull;
+                pl[p][w] |= (v == p + 1 && w == (c >> 6)) ? (1ull << (c & 63)) : 0ull;
+        }
     }
     int alive = 0;
 #pragma unroll
@@ -376,5 +452,12 @@ __global__ void tron_pack_kernel(uint4 *__restrict__ st, long long B, TronParams
     }
     s.terminal = alive <= 1;
     s.ep_len = 0;
-    tron_store(s, st, B, e);
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            uint64_t a = pl[p][2 * j], b = pl[p][2 * j + 1];
+            st[(long long)(3 * p + j) * B + e] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+        }
+    st[(long long)12 * B + e] = tron_hdr_encode(s);
 }
