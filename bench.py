@@ -306,7 +306,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
-    B, K, W = wl["B"], args.steps, args.warmup
+    B, K, W = (args.batch or wl["B"]), args.steps, args.warmup
     per_replica = wl["state"] * B if args.workload != "blokus" else (wl["state"] + 435 * 4) * B
     G = args.replicas or max(2, -(-4 * L2_BYTES // per_replica))       # >= 4 x L2 of state per cycle
     work = {"tron": TronWL, "ttt4": TTTWL, "blokus": BlokusWL}[args.workload](dev, rank, B, G, K)
@@ -420,6 +420,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--replicas", type=int, default=0, help="independent batch replicas per GPU (0 = enough for 4 x L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (exploration only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

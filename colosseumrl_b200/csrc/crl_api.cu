@@ -11,6 +11,7 @@
 #include "../../include/colosseum_b200.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -171,8 +172,13 @@ int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, 
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(tron_step_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (const uint4 *)state_in,
-               (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags);
+    static const bool no_pdl = getenv("CRL_NO_PDL") != nullptr;   // diagnostics: compare with plain stream order
+    if (no_pdl)
+        CRL_LAUNCH(tron_step_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (const uint4 *)state_in,
+                   (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags);
+    else
+        CRL_LAUNCH_PDL(tron_step_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (const uint4 *)state_in,
+                       (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags);
     return check_launch("tron_step_kernel");
 }
 

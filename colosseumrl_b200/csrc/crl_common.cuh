@@ -5,10 +5,24 @@
 #ifndef CRL_HOSTSIM
 #include <cuda_runtime.h>
 #define CRL_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+// launch with the programmatic-stream-serialization attribute (PDL); the kernel must call pdl_wait() before it
+// touches memory written by its predecessor in the stream
+#define CRL_LAUNCH_PDL(kernel, grid_, block_, stream_, ...)                                         \
+    do {                                                                                          \
+        cudaLaunchConfig_t cfg_ = {};                                                             \
+        cfg_.gridDim = dim3(grid_); cfg_.blockDim = dim3(block_); cfg_.dynamicSmemBytes = 0;        \
+        cfg_.stream = (stream_);                                                                  \
+        cudaLaunchAttribute at_[1];                                                               \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                           \
+        at_[0].val.programmaticStreamSerializationAllowed = 1;                                    \
+        cfg_.attrs = at_; cfg_.numAttrs = 1;                                                      \
+        cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                           \
+    } while (0)
 #else
 // tests/hostsim/cuda_shim.h was included first: kernels run on the SIMT emulator (CPU unit tests only)
 #define CRL_LAUNCH(kernel, grid, block, stream, ...) \
     hostsim::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
+#define CRL_LAUNCH_PDL CRL_LAUNCH
 #endif
 
 #define CRL_NSTAT 32
@@ -79,6 +93,18 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
+
+// ---- programmatic dependent launch (PDL): overlap a kernel's launch + prologue with its predecessor's tail ----
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifndef CRL_HOSTSIM
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {   // blocks until the predecessor grid has completed and flushed
+#ifndef CRL_HOSTSIM
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 
 // Episode statistics: per-thread contribution -> warp reduce (redux.sync) -> shared-memory partial per CTA
 // -> one global atomic per CTA and non-zero slot.  Values are small ints; reduce in 32-bit, accumulate in 64.

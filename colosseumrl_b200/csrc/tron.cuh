@@ -142,37 +142,63 @@ __device__ __forceinline__ void tron_new_state(TronTile &tile, int t, TronHdr &s
 
 // One env-step: CyTronGrid.pyx:15-62 (players strictly in index order against the already-updated board),
 // then TronGridEnvironment.py:309-321 and the ranking of :483-508.
+//
+// The reference's loop is sequential in the player index, but the only things a later player can observe from an
+// earlier one in the same step are (a) the single cell it just claimed, (b) its new head and (c) a head-on kill.
+// So all shared-memory lookups are done up front against the OLD board (16 independent loads in flight), the
+// sequential part runs on registers only, and the <= 4 bit sets are independent stores (plane i is written by
+// player i alone).
 __device__ __forceinline__ void tron_step_env(TronTile &tile, int t, TronHdr &s, const int (&act)[4],
                                               const TronParams &prm, TronOut &o) {
     const int N = prm.N, P = prm.P;
+    int nd[4], nx[4], ny[4], own_old[4];
+    bool inb[4], moved[4];
+    uint64_t *wp[4], wold[4], bitm[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        if (i < P && s.death[i] == 0) {                                  // pyx:16
-            int d = (s.dir[i] + act[i] + 4) & 3;                         // pyx:31
-            int x = s.hx[i] + (d == 1) - (d == 3);                       // pyx:34-41
-            int y = s.hy[i] + (d == 2) - (d == 0);
-            s.dir[i] = d;                                                // pyx:44 (also when i dies)
-            if ((unsigned)x >= (unsigned)N || (unsigned)y >= (unsigned)N) {
+        nd[i] = (s.dir[i] + act[i] + 4) & 3;                             // pyx:31
+        nx[i] = s.hx[i] + (nd[i] == 1) - (nd[i] == 3);                   // pyx:34-41
+        ny[i] = s.hy[i] + (nd[i] == 2) - (nd[i] == 0);
+        inb[i] = (unsigned)nx[i] < (unsigned)N && (unsigned)ny[i] < (unsigned)N;
+        const int c = inb[i] ? ny[i] * N + nx[i] : 0, w = c >> 6;
+        bitm[i] = 1ull << (c & 63);
+        own_old[i] = 0;
+        moved[i] = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint64_t *ptr = tron_word(tile, t, q, w);
+            const uint64_t v = *ptr;
+            own_old[i] = (v & bitm[i]) ? q + 1 : own_old[i];
+            if (q == i) { wp[i] = ptr; wold[i] = v; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (i < P && s.death[i] == 0) {                                  // pyx:16 (a head-on kill by j < i counts)
+            s.dir[i] = nd[i];                                            // pyx:44 (also when i dies)
+            if (!inb[i]) {
                 s.death[i] = i + 1;                                      // pyx:47-48
             } else {
-                const int c = y * N + x, w = c >> 6;
-                const uint64_t bit = 1ull << (c & 63);
-                int owner = 0;
+                int owner = own_old[i];
 #pragma unroll
-                for (int q = 0; q < 4; q++) owner = (*tron_word(tile, t, q, w) & bit) ? q + 1 : owner;
+                for (int j = 0; j < i; j++)                              // the cell player j claimed this step
+                    owner = (moved[j] && nx[j] == nx[i] && ny[j] == ny[i]) ? j + 1 : owner;
                 if (owner) {
                     s.death[i] = owner;                                  // pyx:51-53
 #pragma unroll
                     for (int q = 0; q < 4; q++)                          // pyx:56-57 (no liveness check: T3)
-                        if (owner == q + 1 && s.hx[q] == x && s.hy[q] == y) s.death[q] = i + 1;
+                        if (owner == q + 1 && s.hx[q] == nx[i] && s.hy[q] == ny[i]) s.death[q] = i + 1;
                 } else {
-                    *tron_word(tile, t, i, w) |= bit;                    // pyx:60-62
-                    s.hx[i] = x; s.hy[i] = y;
+                    moved[i] = true;                                     // pyx:60-62
+                    s.hx[i] = nx[i]; s.hy[i] = ny[i];
                     s.cells[i] += 1;
                 }
             }
         }
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (moved[i]) *wp[i] = wold[i] | bitm[i];
     int alive = 0;
 #pragma unroll
     for (int p = 0; p < 4; p++) alive |= (p < P && s.death[p] == 0) ? (1 << p) : 0;   // py:310
@@ -190,10 +216,11 @@ __device__ __forceinline__ void tron_step_env(TronTile &tile, int t, TronHdr &s,
 #pragma unroll
     for (int p = 0; p < 4; p++) { score[p] = s.cells[p]; o.cells[p] = s.cells[p]; }
     int tie = 0;  // tie_locations are evaluated up front (py:492); deaths[-1] addresses the LAST player
+    const uint32_t d12 = (uint32_t)s.death[0] | (uint32_t)s.death[1] << 3 | (uint32_t)s.death[2] << 6 | (uint32_t)s.death[3] << 9;
 #pragma unroll
     for (int p = 0; p < 4; p++) {
         int k = s.death[p] ? s.death[p] - 1 : P - 1;
-        if (p < P && tron_sel4(s.death, k) == p + 1) tie |= 1 << p;
+        if (p < P && ((d12 >> (3 * k)) & 7u) == (uint32_t)(p + 1)) tie |= 1 << p;
     }
 #pragma unroll
     for (int p = 0; p < 4; p++) {                                        // py:493-495, ascending, in place
@@ -279,11 +306,13 @@ tron_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const ui
     __shared__ __align__(128) TronTile tile;
     __shared__ __align__(8) uint64_t bar;
     __shared__ int sm_stat[CRL_NSTAT];
+    pdl_launch_dependents();     // let the next launch's CTAs become resident and run their prologue now
     const int t = threadIdx.x;
     const long long e0 = (long long)blockIdx.x * TRON_TILE;
     const int n = (int)min((long long)TRON_TILE, B - e0);
     const bool valid = t < n;
     if (stats && t < CRL_NSTAT) sm_stat[t] = 0;
+    pdl_wait();                  // everything above overlapped with the previous kernel's tail
     const uint32_t a = valid ? actions[e0 + t] : 0u;       // overlaps with the tile's flight
     tron_tile_load(tile, &bar, in, B, e0, n);
     TronOut o;
