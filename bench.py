@@ -171,7 +171,7 @@ class TronWL:
                                                 first_env_id=(rank * G + g) * B) for g in range(G)]
         self.states = [e.new_state()[0] for e in self.envs]
         for e in self.envs[1:]:
-            e.stats = self.envs[0].stats                      # one statistics vector per rank
+            e.stats_rows = self.envs[0].stats_rows                      # one statistics vector per rank
         self.local_t = [0] * G
         self.actions = torch.empty((K, B, 4), dtype=torch.int8, device=dev)   # resident inputs of the timed steps
         self.h_actions = [torch.from_numpy(np.random.RandomState(rank + i).randint(-1, 2, size=(B, 4)).astype(np.int8)).pin_memory()
@@ -218,7 +218,7 @@ class TTTWL:
                                                 first_env_id=(rank * G + g) * B) for g in range(G)]
         self.states = [e.new_state()[0] for e in self.envs]
         for e in self.envs[1:]:
-            e.stats = self.envs[0].stats
+            e.stats_rows = self.envs[0].stats_rows
         self.local_t = [0] * G
         self.h_actions = [torch.from_numpy(np.random.RandomState(rank + i).randint(0, 27, size=(B,)).astype(np.int8)).pin_memory()
                           for i in range(2)]
@@ -254,7 +254,7 @@ class BlokusWL:
                                               first_env_id=(rank * G + g) * B, capacity=2048) for g in range(G)]
         self.states = [e.new_state()[0] for e in self.envs]
         for e in self.envs[1:]:
-            e.stats = self.envs[0].stats
+            e.stats_rows = self.envs[0].stats_rows
         self.local_t = [0] * G
         self.valid = [(torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B, 2048), dtype=torch.int32, device=dev))
                       for _ in range(G)]
@@ -311,6 +311,9 @@ def run_b200(args):
     G = args.replicas or max(2, -(-4 * L2_BYTES // per_replica))       # >= 4 x L2 of state per cycle
     work = {"tron": TronWL, "ttt4": TTTWL, "blokus": BlokusWL}[args.workload](dev, rank, B, G, K)
     stream = torch.cuda.current_stream(dev)
+    if args.no_stats:
+        for e in work.envs:
+            e.collect_stats = False
 
     # warm-up (eager launches through the public API), then capture the K timed steps in one CUDA graph
     k = 0
@@ -420,6 +423,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--replicas", type=int, default=0, help="independent batch replicas per GPU (0 = enough for 4 x L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-stats", action="store_true", help="exploration: skip the fused episode statistics")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (exploration only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

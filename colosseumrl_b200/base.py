@@ -44,7 +44,9 @@ class BatchedBaseEnvironment(ABC):
         self.seed = int(seed)
         self.auto_reset = bool(auto_reset)
         self.first_env_id = int(first_env_id)     # global id of env 0 of this shard (Philox counter)
-        self.stats = torch.zeros(_lib.NSTAT, dtype=torch.int64, device=self.device)
+        # int64 [STAT_ROWS, NSTAT]; partial sums per row, see include/colosseum_b200.h.  `stats` sums the rows.
+        self.stats_rows = torch.zeros((_lib.STAT_ROWS, _lib.NSTAT), dtype=torch.int64, device=self.device)
+        self.collect_stats = True                 # False: the step kernels skip the fused episode statistics
 
     # -- helpers ------------------------------------------------------------------------------------
     @property
@@ -63,6 +65,15 @@ class BatchedBaseEnvironment(ABC):
         if t.device != self.device:
             t = t.to(self.device, non_blocking=True)
         return t.contiguous()
+
+    @property
+    def _stats_ptr(self):
+        return self.stats_rows.data_ptr() if self.collect_stats else None
+
+    @property
+    def stats(self) -> torch.Tensor:
+        """Episode statistics int64 [NSTAT] (slots: include/colosseum_b200.h CRL_ST_*)."""
+        return self.stats_rows.sum(dim=0)
 
     @property
     def flags(self):
@@ -127,7 +138,7 @@ class BatchedBaseEnvironment(ABC):
 
     # -- statistics (fused into the step kernels) ----------------------------------------------------
     def reset_stats(self):
-        self.stats.zero_()
+        self.stats_rows.zero_()
 
     def all_reduce_stats(self) -> torch.Tensor:
         """Sum the episode statistics over all ranks (the only collective of the engine)."""

@@ -83,7 +83,7 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
                    torch.empty((self.batch, self.capacity), dtype=torch.int32, device=self.device))
         counts, ids = out
         self._check(self._lib.crl_blokus_legal(state.packed.data_ptr(), int(player), counts.data_ptr(), ids.data_ptr(),
-                                               ids.shape[1], self.stats.data_ptr() if count_stats else None, self.batch,
+                                               ids.shape[1], self._stats_ptr if count_stats else None, self.batch,
                                                self.flags, self._stream))
         return counts, ids
 
@@ -107,7 +107,7 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         if new.result is None:
             new.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
         self._check(self._lib.crl_blokus_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
-                                              new.result.data_ptr(), self.stats.data_ptr(), self.batch, self.flags,
+                                              new.result.data_ptr(), self._stats_ptr, self.batch, self.flags,
                                               self._stream))
         return new
 

@@ -172,8 +172,8 @@ int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, 
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
-    static const bool no_pdl = getenv("CRL_NO_PDL") != nullptr;   // diagnostics: compare with plain stream order
-    if (no_pdl)
+    static const bool use_pdl = getenv("CRL_PDL") != nullptr;   // diagnostics only: PDL measured slower
+    if (!use_pdl)
         CRL_LAUNCH(tron_step_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (const uint4 *)state_in,
                    (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags);
     else

@@ -26,6 +26,9 @@
 #endif
 
 #define CRL_NSTAT 32
+#define CRL_STAT_ROWS 16   // the device statistics buffer is int64[CRL_STAT_ROWS][CRL_NSTAT]; CTAs spread their
+                           // partial sums over the rows (row = blockIdx % 16) so same-address L2 atomics do not
+                           // serialise; the reader sums the rows
 // statistics slots (int64 each); identical to oracle/oracle_rollout.c
 enum {
     ST_STEPS = 0, ST_EPISODES = 1, ST_EPLEN = 2, ST_WINS = 3 /*..6*/, ST_NOWIN = 7, ST_SCORE = 8 /*..11*/,
@@ -108,6 +111,12 @@ __device__ __forceinline__ void pdl_wait() {   // blocks until the predecessor g
 
 // Episode statistics: per-thread contribution -> warp reduce (redux.sync) -> shared-memory partial per CTA
 // -> one global atomic per CTA and non-zero slot.  Values are small ints; reduce in 32-bit, accumulate in 64.
+// one global atomic per CTA and non-zero slot, into row (blockIdx % CRL_STAT_ROWS); call after a __syncthreads()
+__device__ __forceinline__ void stats_flush_row(const int *sm, crl_u64 *g) {
+    if (threadIdx.x < CRL_NSTAT && sm[threadIdx.x] != 0)
+        atomicAdd(g + (blockIdx.x & (CRL_STAT_ROWS - 1)) * CRL_NSTAT + threadIdx.x, (crl_u64)(long long)sm[threadIdx.x]);
+}
+
 struct BlockStats {
     int *sm;  // __shared__ int[CRL_NSTAT]
     __device__ __forceinline__ void init() const {
@@ -120,6 +129,6 @@ struct BlockStats {
     }
     __device__ __forceinline__ void flush(crl_u64 *g) const {
         __syncthreads();
-        if (threadIdx.x < CRL_NSTAT && sm[threadIdx.x] != 0) atomicAdd(g + threadIdx.x, (crl_u64)(long long)sm[threadIdx.x]);
+        stats_flush_row(sm, g);
     }
 };

@@ -334,7 +334,7 @@ tron_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const ui
     if (stats) {
         tron_stats(sm_stat, valid, o, ep_len);
         __syncthreads();
-        if (t < CRL_NSTAT && sm_stat[t] != 0) atomicAdd(stats + t, (crl_u64)(long long)sm_stat[t]);
+        stats_flush_row(sm_stat, stats);
     }
 }
 
@@ -376,7 +376,7 @@ tron_rollout_kernel(uint4 *__restrict__ state, uint2 *__restrict__ result, crl_u
     tron_tile_store(tile, state, B, e0, n);
     if (stats) {
         __syncthreads();
-        if (t < CRL_NSTAT && sm_stat[t] != 0) atomicAdd(stats + t, (crl_u64)(long long)sm_stat[t]);
+        stats_flush_row(sm_stat, stats);
     }
 }
 

@@ -65,7 +65,7 @@ class _BatchedTicTacToe(BatchedBaseEnvironment):
         if new.valid is None:
             new.valid = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
         self._check(self._lib.crl_ttt_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
-                                           new.result.data_ptr(), new.valid.data_ptr(), self.stats.data_ptr(),
+                                           new.result.data_ptr(), new.valid.data_ptr(), self._stats_ptr,
                                            self.batch, self.N_PLAYERS, self.flags, self._stream))
         return new
 
@@ -120,7 +120,7 @@ class _BatchedTicTacToe(BatchedBaseEnvironment):
         if state.result is None:
             state.result = torch.empty((self.batch, 4), dtype=torch.uint8, device=self.device)
         state.valid = None
-        self._check(self._lib.crl_ttt_rollout(state.packed.data_ptr(), state.result.data_ptr(), self.stats.data_ptr(),
+        self._check(self._lib.crl_ttt_rollout(state.packed.data_ptr(), state.result.data_ptr(), self._stats_ptr,
                                               self.seed, self.first_env_id, int(step0), int(K), self.batch,
                                               self.N_PLAYERS, self._stream))
         return state

@@ -97,7 +97,7 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         if new.result is None:
             new.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
         self._check(self._lib.crl_tron_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
-                                            new.result.data_ptr(), self.stats.data_ptr(), self.batch, self.N,
+                                            new.result.data_ptr(), self._stats_ptr, self.batch, self.N,
                                             self.num_players, self.flags, self._stream))
         return new
 
@@ -150,7 +150,7 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         """K random-policy steps with auto-reset in one launch (state updated in place)."""
         if state.result is None:
             state.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
-        self._check(self._lib.crl_tron_rollout(state.packed.data_ptr(), state.result.data_ptr(), self.stats.data_ptr(),
+        self._check(self._lib.crl_tron_rollout(state.packed.data_ptr(), state.result.data_ptr(), self._stats_ptr,
                                                self.seed, self.first_env_id, int(step0), int(K), self.batch, self.N,
                                                self.num_players, self._stream))
         return state

@@ -31,8 +31,11 @@ extern "C" {
 
 #define CRL_FLAG_AUTO_RESET 1 /* an environment whose stored terminal flag is set is replaced by new_state() before the step */
 
-/* statistics vector: int64[CRL_NSTAT] on the device, accumulated (+=) by step / rollout kernels */
+/* statistics buffer: int64[CRL_STAT_ROWS][CRL_NSTAT] on the device, accumulated (+=) by step / rollout kernels.
+ * CTAs spread their partial sums over the rows so that same-address L2 atomics do not serialise; the value of
+ * slot s is the sum over rows of stats[row][s]. */
 #define CRL_NSTAT 32
+#define CRL_STAT_ROWS 16
 #define CRL_ST_STEPS 0     /* env-steps                                   */
 #define CRL_ST_EPISODES 1  /* finished episodes (terminal transitions)    */
 #define CRL_ST_EPLEN 2     /* sum of finished-episode lengths             */

@@ -145,7 +145,7 @@ def case_rollout_vs_oracle(be, B=24, K=80, seed=3, env0=500, cap=2048):
     ob = orc.BlokusBatch(B)
     ob.rollout(seed, env0, 0, K, fresh=True)
     st, st2 = be.zeros((B, 22, 4), np.int32), be.zeros((B, 22, 4), np.int32)
-    stats = be.zeros((32,), np.int64)
+    stats = be.zeros((16, 32), np.int64)
     counts, ids = be.zeros((B,), np.int32), be.zeros((B, cap), np.int32)
     act, res = be.zeros((B,), np.int32), be.zeros((B, 8), np.uint8)
     be.check(be.lib.crl_blokus_reset(be.ptr(st), None, B, be.stream))
@@ -159,7 +159,7 @@ def case_rollout_vs_oracle(be, B=24, K=80, seed=3, env0=500, cap=2048):
     assert (board == ob.board).all() and (pieces == ob.inventory).all() and (score == ob.scores).all()
     assert (meta[:, 0] == ob.round_count).all() and (meta[:, 1] == ob.mover).all()
     assert (meta[:, 2] == ob.terminal).all() and (meta[:, 3] == ob.ep_len).all()
-    s = be.download(stats)
+    s = be.download(stats).sum(0)
     assert (s == ob.stats).all(), (s, ob.stats)
     assert int(be.download(counts).max()) <= cap
 

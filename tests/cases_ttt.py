@@ -80,7 +80,7 @@ def case_rollout_vs_oracle(be, n, B=300, K=40, seed=4, env0=77):
     ob = orc.TTTBatch(B, n)
     ob.rollout(seed, env0, 0, K, fresh=True)
     st, st2 = be.zeros((B, 4), np.int32), be.zeros((B, 4), np.int32)
-    stats = be.zeros((32,), np.int64)
+    stats = be.zeros((16, 32), np.int64)
     act, res = be.zeros((B,), np.int8), be.zeros((B, 4), np.uint8)
     be.check(be.lib.crl_ttt_reset(be.ptr(st), None, B, n, be.stream))
     cur, nxt = st, st2
@@ -90,15 +90,15 @@ def case_rollout_vs_oracle(be, n, B=300, K=40, seed=4, env0=77):
         cur, nxt = nxt, cur
     board, winner, mover = ttt_unpack(be, cur, n)
     assert (board.reshape(ob.board.shape) == ob.board).all() and (winner == ob.winner).all() and (mover == ob.mover).all()
-    s = be.download(stats)
+    s = be.download(stats).sum(0)
     assert (s == ob.stats).all(), (s, ob.stats)
     term = unpack_result(be.download(res))["terminal"]
     assert (term == ob.terminal.astype(bool)).all()
-    st3, stats3 = be.zeros((B, 4), np.int32), be.zeros((32,), np.int64)
+    st3, stats3 = be.zeros((B, 4), np.int32), be.zeros((16, 32), np.int64)
     be.check(be.lib.crl_ttt_reset(be.ptr(st3), None, B, n, be.stream))
     be.check(be.lib.crl_ttt_rollout(be.ptr(st3), None, be.ptr(stats3), seed, env0, 0, 7, B, n, be.stream))
     be.check(be.lib.crl_ttt_rollout(be.ptr(st3), be.ptr(res), be.ptr(stats3), seed, env0, 7, K - 7, B, n, be.stream))
-    assert (be.download(st3) == be.download(cur)).all() and (be.download(stats3) == ob.stats).all()
+    assert (be.download(st3) == be.download(cur)).all() and (be.download(stats3).sum(0) == ob.stats).all()
 
 
 def case_masked_reset_and_errors(be):
