@@ -257,9 +257,12 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
             }
         }
         // terminal test on the OLD board / OLD round with the NEW inventories (BlokusEnvironment.py:424)
+        // `any` is order-independent; start with the players that have not moved yet this round (in round 0 the
+        // ones that already moved have an occupied corner and would need a full, fruitless scan) and end with the mover.
         int any = 0;
 #pragma unroll 1
-        for (int q = 0; q < 4 && !any; q++) {
+        for (int j = 1; j <= 4 && !any; j++) {
+            const int q = (mover + j) & 3;
             uint32_t iq = 0;
 #pragma unroll
             for (int r = 0; r < 4; r++) iq |= (r == q) ? inv[r] : 0u;
