@@ -333,6 +333,7 @@ def run_b200(args):
 
     clocks = ClockSampler(local)
     if world > 1:
+        work.stats_env.all_reduce_stats()          # warm-up: NCCL communicator setup happens on the first collective
         dist.barrier()
     torch.cuda.synchronize()
     clocks.start()
