@@ -37,8 +37,8 @@ class BlokusBatchState:
 
 class BatchedBlokusEnvironment(BatchedBaseEnvironment):
     def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
-                 first_env_id: int = 0, capacity: int = 2048):
-        super().__init__(config, batch, device, seed, auto_reset, first_env_id)
+                 first_env_id: int = 0, capacity: int = 2048, host_io: bool = False):
+        super().__init__(config, batch, device, seed, auto_reset, first_env_id, host_io)
         self.capacity = int(capacity)      # slots per game in the valid-action list (reference max observed: 1753)
 
     @property
@@ -105,7 +105,7 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         actions = self._dev(actions, torch.int32)
         new = out if out is not None else BlokusBatchState(self._alloc())
         if new.result is None:
-            new.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
+            new.result = self._new_result((self.batch, 8))
         self._check(self._lib.crl_blokus_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
                                               new.result.data_ptr(), self._stats_ptr, self.batch, self.flags,
                                               self._stream))

@@ -61,7 +61,7 @@ class _BatchedTicTacToe(BatchedBaseEnvironment):
         actions = self._dev(actions, torch.int8)
         new = out if out is not None else TTTBatchState(torch.empty_like(state.packed))
         if new.result is None:
-            new.result = torch.empty((self.batch, 4), dtype=torch.uint8, device=self.device)
+            new.result = self._new_result((self.batch, 4))
         if new.valid is None:
             new.valid = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
         self._check(self._lib.crl_ttt_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
@@ -118,7 +118,7 @@ class _BatchedTicTacToe(BatchedBaseEnvironment):
 
     def rollout(self, state: TTTBatchState, step0: int, K: int) -> TTTBatchState:
         if state.result is None:
-            state.result = torch.empty((self.batch, 4), dtype=torch.uint8, device=self.device)
+            state.result = self._new_result((self.batch, 4))
         state.valid = None
         self._check(self._lib.crl_ttt_rollout(state.packed.data_ptr(), state.result.data_ptr(), self._stats_ptr,
                                               self.seed, self.first_env_id, int(step0), int(K), self.batch,

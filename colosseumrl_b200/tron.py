@@ -39,8 +39,8 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
     ACTIONS = ["forward", "right", "left"]
 
     def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
-                 first_env_id: int = 0):
-        super().__init__(config, batch, device, seed, auto_reset, first_env_id)
+                 first_env_id: int = 0, host_io: bool = False):
+        super().__init__(config, batch, device, seed, auto_reset, first_env_id, host_io)
         self.N, self.num_players, self.observation_window, self.remove_on_death = parse_tron_config(config)
         if self._lib.crl_tron_state_bytes(self.N, self.num_players, self.batch) < 0:
             raise _lib.CrlError(self._lib.crl_last_error().decode())
@@ -95,7 +95,7 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
             raise ValueError("actions must have shape [B, 4]")
         new = out if out is not None else TronBatchState(self._alloc())
         if new.result is None:
-            new.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
+            new.result = self._new_result((self.batch, 8))
         self._check(self._lib.crl_tron_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
                                             new.result.data_ptr(), self._stats_ptr, self.batch, self.N,
                                             self.num_players, self.flags, self._stream))
@@ -111,7 +111,7 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
     def is_terminal(self, state: TronBatchState) -> torch.Tensor:
         if state.result is not None:
             return state.result[:, 4]
-        return ((state.packed[12, :, 2] >> 20) & 1).to(torch.uint8)
+        return ((state.packed[12, :, 1] >> 30) & 1).to(torch.uint8)
 
     def compute_ranking(self, state: TronBatchState, players=None, winners=None) -> torch.Tensor:
         """TronGridEnvironment.compute_ranking (:483-508), fused into the step: uint8 [B, P]."""
@@ -149,7 +149,7 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
     def rollout(self, state: TronBatchState, step0: int, K: int) -> TronBatchState:
         """K random-policy steps with auto-reset in one launch (state updated in place)."""
         if state.result is None:
-            state.result = torch.empty((self.batch, 8), dtype=torch.uint8, device=self.device)
+            state.result = self._new_result((self.batch, 8))
         self._check(self._lib.crl_tron_rollout(state.packed.data_ptr(), state.result.data_ptr(), self._stats_ptr,
                                                self.seed, self.first_env_id, int(step0), int(K), self.batch, self.N,
                                                self.num_players, self._stream))
