@@ -28,6 +28,37 @@ import torch
 from . import _lib
 
 
+class HostStepper:
+    """One env-step for an actor whose policy runs on the HOST, as a single CUDA-graph launch:
+    H2D copy of `actions` (pinned) -> step kernel (in place on `state`) -> D2H copy of the result record (pinned).
+
+        stepper = env.host_stepper(state)
+        stepper.actions[...] = my_policy(...)      # write into the pinned action buffer
+        result = stepper()                         # replay + wait; `result` is the pinned uint8 record tensor
+
+    Zero-copy access to pinned memory from the kernel was measured ~4x slower than explicit copies (PCIe posted
+    8-byte writes), so the copies stay explicit and the three operations are fused into one graph launch instead.
+    """
+
+    def __init__(self, env, state, action_shape, action_dtype):
+        self.env, self.state = env, state
+        self.actions = torch.zeros(action_shape, dtype=action_dtype).pin_memory()
+        self._dev_actions = torch.zeros(action_shape, dtype=action_dtype, device=env.device)
+        env.step_(state, self._dev_actions, out=state)          # allocates state.result; warms the launch path
+        self.result = torch.empty(state.result.shape, dtype=torch.uint8).pin_memory()
+        torch.cuda.synchronize(env.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._dev_actions.copy_(self.actions, non_blocking=True)
+            env.step_(state, self._dev_actions, out=state)
+            self.result.copy_(state.result, non_blocking=True)
+
+    def __call__(self):
+        self.graph.replay()
+        torch.cuda.current_stream(self.env.device).synchronize()
+        return self.result
+
+
 class BatchedBaseEnvironment(ABC):
     def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
                  first_env_id: int = 0, host_io: bool = False):

@@ -101,6 +101,12 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
                                             self.num_players, self.flags, self._stream))
         return new
 
+    def host_stepper(self, state: TronBatchState):
+        """Graph-fused H2D actions -> step -> D2H result for host-side policies (see base.HostStepper).
+        NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
+        from .base import HostStepper
+        return HostStepper(self, state, (self.batch, 4), torch.int8)
+
     def valid_actions(self, state, player):
         """Always ['forward', 'right', 'left'] (:325-341): uint8 [B, 3] of ones."""
         return torch.ones((self.batch, 3), dtype=torch.uint8, device=self.device)

@@ -131,3 +131,23 @@ def test_host_io_zero_copy_mode():
     s, p, r, term, w = e.next_state(s, None, torch.arange(64, dtype=torch.int8).remainder(15).pin_memory())
     torch.cuda.synchronize()
     assert s.result.is_pinned() and (e.state_arrays(s)[0].reshape(64, 15).cpu().numpy() >= 0).sum() == 64
+
+
+def test_host_stepper_matches_next_state():
+    """host_stepper (graph-fused H2D + step + D2H) == next_state with the same actions."""
+    from colosseumrl_b200.tron import BatchedTronGridEnvironment
+    B = 777
+    a_env = BatchedTronGridEnvironment("", batch=B, seed=3)
+    b_env = BatchedTronGridEnvironment("", batch=B, seed=3)
+    sa, _ = a_env.new_state()
+    sb, _ = b_env.new_state()
+    stepper = b_env.host_stepper(sb)                      # warm-up applies one all-forward step
+    sa, *_ = a_env.next_state(sa, None, torch.zeros((B, 4), dtype=torch.int8))
+    rng = np.random.RandomState(0)
+    for t in range(12):
+        a = torch.from_numpy(rng.randint(-1, 2, size=(B, 4)).astype(np.int8))
+        sa, pa, ra, ta, wa = a_env.next_state(sa, None, a)
+        stepper.actions.copy_(a)
+        res = stepper()
+        assert res.is_pinned() and (res == sa.result.cpu()).all()
+    assert (sa.packed == sb.packed).all()
