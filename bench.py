@@ -15,10 +15,9 @@ How it is timed
   * value: the K timed steps are captured in ONE CUDA graph (the step is a few microseconds, Python launch
     overhead would dominate) and replayed between two CUDA events on the launching stream; barrier +
     synchronize on both sides; max over ranks.  ms_per_step = elapsed / K.
-  * e2e: through the public Python API (Batched*Environment.next_state, host_io mode) with HOST buffers: per step
-    the kernel reads the actions from pinned host memory and writes the result record to pinned host memory
-    (zero-copy over PCIe, so both transfers are inside the timed step), and the host waits for the result before
-    issuing the next step (the loop an actor with a host-side policy runs).
+  * e2e: through the public Python API for host-side policies (env.host_stepper: one CUDA-graph launch = H2D copy
+    of the pinned actions + step kernel + D2H copy of the result record into pinned memory); the host waits for the
+    result before issuing the next step (the loop an actor with a host-side policy runs).
   * roofline: algorithmic bytes per env-step x envs per launch / mean launch duration
     (elapsed / K, so launch gaps count against us) vs the measured copy bandwidth in MEASURED_PEAKS.json.
   * cpu_baseline / --impl reference: the CPU oracle port (oracle/liboracle.so: plain-C restatement of the
@@ -178,12 +177,7 @@ class TronWL:
         self.h_actions = [torch.from_numpy(np.random.RandomState(rank + i).randint(-1, 2, size=(B, 4)).astype(np.int8)).pin_memory()
                           for i in range(2)]
         self.h2d, self.d2h = B * 4, B * 8
-        # e2e: host-I/O mode of the public API (pinned action tensors read in place by the kernel, result records
-        # written straight into pinned host memory); the packed state tensors are shared with the replicas above
-        from colosseumrl_b200.tron import TronBatchState
-        self.e2e_env = BatchedTronGridEnvironment("", batch=B, device=dev, seed=0, auto_reset=True, host_io=True)
-        self.e2e_env.stats_rows = self.envs[0].stats_rows
-        self.e2e_states = [TronBatchState(st.packed) for st in self.states]
+        self.steppers = None
 
     def prepare(self, k0, K):
         """Pre-generate the actions of timed steps k0..k0+K-1 (Philox policy kernel), outside the timed region."""
@@ -204,10 +198,14 @@ class TronWL:
         env.step_(st, act, out=st)                             # in place; C-ABI crl_tron_step
 
     def e2e_step(self, k):
-        st = self.e2e_states[k % self.G]
-        new, alive, rewards, terminal, winners = self.e2e_env.next_state(st, None, self.h_actions[k & 1], out=st)
-        self.torch.cuda.current_stream().synchronize()         # the host consumes the result before the next step
-        return int(terminal[0])                                # (host tensors: views of the pinned result record)
+        if self.steppers is None:       # public API for host-side policies: one graph launch = H2D + step + D2H
+            self.steppers = [e.host_stepper(s) for e, s in zip(self.envs, self.states)]
+            for sp in self.steppers:
+                sp()                    # the first replay of a graph uploads it: keep that out of the timing
+        sp = self.steppers[k % self.G]
+        sp.actions.copy_(self.h_actions[k & 1])                # the host policy writes its actions (host memcpy)
+        result = sp()                                          # replay + wait: the host consumes the result record
+        return int(result[0, 4])
 
     @property
     def stats_env(self):
@@ -228,10 +226,7 @@ class TTTWL:
         self.h_actions = [torch.from_numpy(np.random.RandomState(rank + i).randint(0, 27, size=(B,)).astype(np.int8)).pin_memory()
                           for i in range(2)]
         self.h2d, self.d2h = B, B * 4
-        from colosseumrl_b200.tictactoe import TTTBatchState
-        self.e2e_env = BatchedTicTacToe4PlayerEnv("", batch=B, device=dev, seed=0, auto_reset=True, host_io=True)
-        self.e2e_env.stats_rows = self.envs[0].stats_rows
-        self.e2e_states = [TTTBatchState(st.packed) for st in self.states]
+        self.steppers = None
 
     def prepare(self, k0, K):
         pass
@@ -242,10 +237,14 @@ class TTTWL:
         self.local_t[g] += 1
 
     def e2e_step(self, k):
-        st = self.e2e_states[k % self.G]
-        new = self.e2e_env.step_(st, self.h_actions[k & 1], out=st)       # result record lands in pinned host memory
-        self.torch.cuda.current_stream().synchronize()
-        return int(new.result[0, 1])
+        if self.steppers is None:
+            self.steppers = [e.host_stepper(s) for e, s in zip(self.envs, self.states)]
+            for sp in self.steppers:
+                sp()
+        sp = self.steppers[k % self.G]
+        sp.actions.copy_(self.h_actions[k & 1])
+        result = sp()
+        return int(result[0, 1])
 
     @property
     def stats_env(self):

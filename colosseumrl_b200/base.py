@@ -61,7 +61,7 @@ class HostStepper:
 
 class BatchedBaseEnvironment(ABC):
     def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
-                 first_env_id: int = 0, host_io: bool = False):
+                 first_env_id: int = 0):
         self._config = config
         self.batch = int(batch)
         self.device = torch.device(device)
@@ -75,10 +75,6 @@ class BatchedBaseEnvironment(ABC):
         self.seed = int(seed)
         self.auto_reset = bool(auto_reset)
         self.first_env_id = int(first_env_id)     # global id of env 0 of this shard (Philox counter)
-        # host_io: for actors whose policy runs on the host.  Result records are allocated in pinned (mapped) host
-        # memory and written there directly by the step kernel, and pinned action tensors are read in place by
-        # the kernel (zero-copy over PCIe): one launch + one stream synchronize per step, no separate copies.
-        self.host_io = bool(host_io)
         # int64 [STAT_ROWS, NSTAT]; partial sums per row, see include/colosseum_b200.h.  `stats` sums the rows.
         self.stats_rows = torch.zeros((_lib.STAT_ROWS, _lib.NSTAT), dtype=torch.int64, device=self.device)
         self.collect_stats = True                 # False: the step kernels skip the fused episode statistics
@@ -97,16 +93,12 @@ class BatchedBaseEnvironment(ABC):
             t = torch.as_tensor(t)
         if t.dtype != dtype:
             t = t.to(dtype)
-        if self.host_io and t.device.type == "cpu" and t.is_pinned():
-            return t.contiguous()                 # unified addressing: the kernel reads the pinned buffer in place
         if t.device != self.device:
             t = t.to(self.device, non_blocking=True)
         return t.contiguous()
 
     def _new_result(self, shape):
-        """Result-record tensor: device memory, or pinned host memory in host_io mode."""
-        if self.host_io:
-            return torch.empty(shape, dtype=torch.uint8).pin_memory()
+        """Result-record tensor (device memory)."""
         return torch.empty(shape, dtype=torch.uint8, device=self.device)
 
     @property

@@ -37,8 +37,8 @@ class BlokusBatchState:
 
 class BatchedBlokusEnvironment(BatchedBaseEnvironment):
     def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
-                 first_env_id: int = 0, capacity: int = 2048, host_io: bool = False):
-        super().__init__(config, batch, device, seed, auto_reset, first_env_id, host_io)
+                 first_env_id: int = 0, capacity: int = 2048):
+        super().__init__(config, batch, device, seed, auto_reset, first_env_id)
         self.capacity = int(capacity)      # slots per game in the valid-action list (reference max observed: 1753)
 
     @property

@@ -39,8 +39,8 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
     ACTIONS = ["forward", "right", "left"]
 
     def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
-                 first_env_id: int = 0, host_io: bool = False):
-        super().__init__(config, batch, device, seed, auto_reset, first_env_id, host_io)
+                 first_env_id: int = 0):
+        super().__init__(config, batch, device, seed, auto_reset, first_env_id)
         self.N, self.num_players, self.observation_window, self.remove_on_death = parse_tron_config(config)
         if self._lib.crl_tron_state_bytes(self.N, self.num_players, self.batch) < 0:
             raise _lib.CrlError(self._lib.crl_last_error().decode())

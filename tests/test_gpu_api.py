@@ -108,31 +108,6 @@ def test_blokus_api():
         assert (o["score"][e].cpu().numpy() == oo["score"]).all()
 
 
-def test_host_io_zero_copy_mode():
-    """host_io: pinned action tensors are read in place and result records land in pinned host memory."""
-    from colosseumrl_b200.tron import BatchedTronGridEnvironment
-    from colosseumrl_b200.tictactoe import BatchedTicTacToe3PlayerEnv
-    B = 1000
-    dev = BatchedTronGridEnvironment("", batch=B, seed=3)
-    hst = BatchedTronGridEnvironment("", batch=B, seed=3, host_io=True)
-    sd, _ = dev.new_state()
-    sh, _ = hst.new_state()
-    rng = np.random.RandomState(0)
-    for t in range(15):
-        a = torch.from_numpy(rng.randint(-1, 2, size=(B, 4)).astype(np.int8)).pin_memory()
-        sd, pd, rd, td, wd = dev.next_state(sd, None, a)
-        sh, ph, rh, th, wh = hst.next_state(sh, None, a)
-        torch.cuda.synchronize()
-        assert rh.device.type == "cpu" and sh.result.is_pinned()
-        assert (rd.cpu() == rh).all() and (td.cpu() == th).all() and (wd.cpu() == wh).all() and (pd.cpu() == ph).all()
-    assert (sd.packed == sh.packed).all()
-    e = BatchedTicTacToe3PlayerEnv(batch=64, host_io=True)
-    s, _ = e.new_state()
-    s, p, r, term, w = e.next_state(s, None, torch.arange(64, dtype=torch.int8).remainder(15).pin_memory())
-    torch.cuda.synchronize()
-    assert s.result.is_pinned() and (e.state_arrays(s)[0].reshape(64, 15).cpu().numpy() >= 0).sum() == 64
-
-
 def test_host_stepper_matches_next_state():
     """host_stepper (graph-fused H2D + step + D2H) == next_state with the same actions."""
     from colosseumrl_b200.tron import BatchedTronGridEnvironment
