@@ -302,8 +302,10 @@ int crl_ttt_step(const void *state_in, void *state_out, const int8_t *actions, u
     if (rc) return rc;
     if (!state_in || !state_out || !actions || !result || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_step: bad argument%s");
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(ttt_step_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state_in, (uint4 *)state_out,
-               actions, (uint32_t *)result, valid_after, (crl_u64 *)stats, (long long)B, prm, flags);
+#define TTT_STEP(NP) CRL_LAUNCH(ttt_step_kernel<NP>, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state_in, \
+                               (uint4 *)state_out, actions, (uint32_t *)result, valid_after, (crl_u64 *)stats, (long long)B, flags)
+    if (n == 2) TTT_STEP(2); else if (n == 3) TTT_STEP(3); else TTT_STEP(4);
+#undef TTT_STEP
     return check_launch("ttt_step_kernel");
 }
 
@@ -324,8 +326,10 @@ int crl_ttt_policy_random(const void *state, int8_t *actions, uint64_t seed, uin
     if (rc) return rc;
     if (!state || !actions || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_policy_random: bad argument%s");
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(ttt_policy_random_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state, actions,
-               (long long)B, prm, flags, (crl_u64)seed, (crl_u64)first_env, step);
+#define TTT_POL(NP) CRL_LAUNCH(ttt_policy_random_kernel<NP>, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state, \
+                              actions, (long long)B, flags, (crl_u64)seed, (crl_u64)first_env, step)
+    if (n == 2) TTT_POL(2); else if (n == 3) TTT_POL(3); else TTT_POL(4);
+#undef TTT_POL
     return check_launch("ttt_policy_random_kernel");
 }
 
@@ -336,8 +340,10 @@ int crl_ttt_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed,
     if (rc) return rc;
     if (!state || B < 0 || K < 0) return fail(CRL_ERR_ARG, "crl_ttt_rollout: bad argument%s");
     if (B == 0 || K == 0) return CRL_OK;
-    CRL_LAUNCH(ttt_rollout_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint4 *)state, (uint32_t *)result,
-               (crl_u64 *)stats, (long long)B, prm, (crl_u64)seed, (crl_u64)first_env, step0, K);
+#define TTT_ROLL(NP) CRL_LAUNCH(ttt_rollout_kernel<NP>, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint4 *)state, \
+                               (uint32_t *)result, (crl_u64 *)stats, (long long)B, (crl_u64)seed, (crl_u64)first_env, step0, K)
+    if (n == 2) TTT_ROLL(2); else if (n == 3) TTT_ROLL(3); else TTT_ROLL(4);
+#undef TTT_ROLL
     return check_launch("ttt_rollout_kernel");
 }
 

@@ -21,6 +21,7 @@
 #pragma once
 #include "crl_common.cuh"
 #include "philox.cuh"
+#include "ttt_tables.h"
 
 #define TTT_MAX_DIRS 13
 
@@ -56,35 +57,31 @@ __device__ __forceinline__ uint4 ttt_encode(const TTTEnv &s) {
 __device__ __forceinline__ void ttt_new_state(TTTEnv &s) {
     s.m[0] = s.m[1] = s.m[2] = s.m[3] = 0; s.mover = 0; s.winner1 = 0; s.ep_len = 0;
 }
-__device__ __forceinline__ bool ttt_is_terminal(const TTTEnv &s, const TTTParams &prm) {
-    return s.winner1 != 0 || ((s.m[0] | s.m[1] | s.m[2] | s.m[3]) == prm.cellmask);
-}
-__device__ __forceinline__ bool ttt_has_line(uint32_t m, const TTTParams &prm) {
-    uint32_t hit = 0;
-#pragma unroll
-    for (int d = 0; d < TTT_MAX_DIRS; d++)
-        if (d < prm.ndirs) hit |= m & (m >> prm.stride[d]) & (m >> (2 * prm.stride[d])) & prm.start[d];
-    return hit != 0;
+template <int NP>
+__device__ __forceinline__ bool ttt_is_terminal(const TTTEnv &s) {
+    return s.winner1 != 0 || ((s.m[0] | s.m[1] | s.m[2] | s.m[3]) == TTTGeo<NP>::CELLMASK);
 }
 
 // next_state (tictactoe_2p_env.py:283-315).  action: C-order flat cell index, negative = '' (pass).
-__device__ __forceinline__ void ttt_step_env(TTTEnv &s, int action, const TTTParams &prm, TTTOut &o) {
+template <int NP>
+__device__ __forceinline__ void ttt_step_env(TTTEnv &s, int action, TTTOut &o) {
+    constexpr uint32_t CELLMASK = TTTGeo<NP>::CELLMASK;
     uint32_t occ = s.m[0] | s.m[1] | s.m[2] | s.m[3];
-    o.nvalid = __popc(~occ & prm.cellmask);
-    bool in_range = action >= 0 && action < prm.cells;
-    uint32_t bit = in_range ? (1u << action) : 0u;
-    bool cell_free = in_range && !(occ & bit);                       // is_valid_action (:350-380)
-    bool placed = cell_free && s.winner1 == 0;                       // :293
+    o.nvalid = __popc(~occ & CELLMASK);
+    const bool in_range = (unsigned)action < (unsigned)TTTGeo<NP>::CELLS;
+    const uint32_t bit = in_range ? (1u << action) : 0u;
+    const bool cell_free = in_range && !(occ & bit);                 // is_valid_action (:350-380)
+    const bool placed = cell_free && s.winner1 == 0;                 // :293
     o.error = (action >= 0 && !cell_free) ? 1 : 0;                   // invalid action: silent no-op in the reference
     o.placed = placed;
     if (placed) {
         uint32_t mine = 0;
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
+        for (int p = 0; p < NP; p++) {
             s.m[p] |= (p == s.mover) ? bit : 0u;                     // :295
             mine |= (p == s.mover) ? s.m[p] : 0u;
         }
-        if (ttt_has_line(mine, prm)) s.winner1 = s.mover + 1;        // :297-300
+        if (TTTGeo<NP>::win(mine)) s.winner1 = s.mover + 1;          // :297-300
         occ |= bit;
     }
     o.reward = 0; o.terminal = 0; o.winners = 0;
@@ -93,34 +90,57 @@ __device__ __forceinline__ void ttt_step_env(TTTEnv &s, int action, const TTTPar
         o.winners = 1 << (s.winner1 - 1);
         o.terminal = 1;
     }
-    if (occ == prm.cellmask) o.terminal = 1;                         // :310-311 draw / full board
-    o.valid_after = ~occ & prm.cellmask;
-    s.mover = (s.mover + 1 == prm.n) ? 0 : s.mover + 1;              // :313
+    if (occ == CELLMASK) o.terminal = 1;                             // :310-311 draw / full board
+    o.valid_after = ~occ & CELLMASK;
+    s.mover = (s.mover + 1 == NP) ? 0 : s.mover + 1;                 // :313
     s.ep_len += 1;
 }
 
 // result record, 4 bytes: int8 reward | u8 flags (1 terminal, 2 invalid action, 4 placed) | u8 winners mask |
 // u8 ranking bits (bit p = rank of player p: winners 0, everybody else 1 -- BaseEnvironment.py:173-195)
-__device__ __forceinline__ uint32_t ttt_pack_result(const TTTOut &o, const TTTParams &prm) {
-    uint32_t rank = ((1u << prm.n) - 1u) & ~(uint32_t)o.winners;
+template <int NP>
+__device__ __forceinline__ uint32_t ttt_pack_result(const TTTOut &o) {
+    uint32_t rank = ((1u << NP) - 1u) & ~(uint32_t)o.winners;
     return ((uint32_t)o.reward & 0xffu) | (uint32_t)(o.terminal | o.error << 1 | o.placed << 2) << 8 |
            (uint32_t)o.winners << 16 | rank << 24;
 }
 
-__device__ __forceinline__ void ttt_stats(const BlockStats &bs, bool valid, const TTTOut &o, int mover,
-                                          uint32_t ep_len, const TTTParams &prm) {
-    int t = valid && o.terminal;
-    bs.add(ST_STEPS, valid ? 1 : 0);
-    bs.add(ST_EPISODES, t);
-    bs.add(ST_EPLEN, t ? (int)ep_len : 0);
-    bs.add(ST_NOWIN, t && o.winners == 0);
-    bs.add(ST_ERRORS, valid ? o.error : 0);
-    bs.add(ST_NVALID, valid ? o.nvalid : 0);
-    bs.add(ST_REWARD, valid ? (mover + 1) * o.reward : 0);
+// Episode statistics of one step: 15 counters packed into 4 words -> 4 redux.sync per warp; lane 0 adds the
+// packed warp sums into per-warp shared slots (plain stores, one slot per warp) that are unpacked once per CTA.
+struct TTTStatAcc {
+    uint32_t a, b, c, d;   // running packed sums of this warp (lane 0 only)
+};
+template <int NP>
+__device__ __forceinline__ void ttt_stats(TTTStatAcc &acc, bool valid, const TTTOut &o, int mover, uint32_t ep_len) {
+    const uint32_t t = (valid && o.terminal) ? 1u : 0u;
+    const uint32_t w = t ? (uint32_t)o.winners : 0u, r = t ? (((1u << NP) - 1u) & ~(uint32_t)o.winners) : 0u;
+    // fields hold sums over <= 32 lanes: 8-bit fields for 0/1 values, wider ones where needed
+    uint32_t A = (valid ? 1u : 0u) | t << 8 | (t & (o.winners == 0)) << 16 | (valid ? (uint32_t)o.error : 0u) << 24;
+    uint32_t Bw = (w & 1u) | (w >> 1 & 1u) << 8 | (w >> 2 & 1u) << 16 | (w >> 3 & 1u) << 24;
+    uint32_t C = (r & 1u) | (r >> 1 & 1u) << 8 | (r >> 2 & 1u) << 16 | (r >> 3 & 1u) << 24;
+    uint32_t D = (valid ? (uint32_t)o.nvalid : 0u) | (t ? min(ep_len, 31u) : 0u) << 10 |
+                 (uint32_t)((valid ? (mover + 1) * o.reward : 0) + 4) << 20;           // reward biased by +4 per lane
+    A = __reduce_add_sync(0xffffffffu, A); Bw = __reduce_add_sync(0xffffffffu, Bw);
+    C = __reduce_add_sync(0xffffffffu, C); D = __reduce_add_sync(0xffffffffu, D);
+    acc.a = A; acc.b = Bw; acc.c = C; acc.d = D;
+}
+// add one step's packed warp sums into the CTA's shared counters (lane 0 of each warp)
+__device__ __forceinline__ void ttt_stats_commit(int *sm_stat, const TTTStatAcc &acc) {
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sm_stat[ST_STEPS], (int)(acc.a & 255u));
+        atomicAdd(&sm_stat[ST_NVALID], (int)(acc.d & 1023u));
+        atomicAdd(&sm_stat[ST_REWARD], (int)(acc.d >> 20) - 4 * 32);
+        if (acc.a >> 24) atomicAdd(&sm_stat[ST_ERRORS], (int)(acc.a >> 24));
+        if (acc.a >> 8 & 255u) {
+            atomicAdd(&sm_stat[ST_EPISODES], (int)(acc.a >> 8 & 255u));
+            atomicAdd(&sm_stat[ST_NOWIN], (int)(acc.a >> 16 & 255u));
+            atomicAdd(&sm_stat[ST_EPLEN], (int)(acc.d >> 10 & 1023u));
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-        bs.add(ST_WINS + p, t ? (o.winners >> p & 1) : 0);
-        bs.add(ST_RANK + p, (t && p < prm.n) ? (~o.winners >> p & 1) : 0);
+            for (int p = 0; p < 4; p++) {
+                atomicAdd(&sm_stat[ST_WINS + p], (int)(acc.b >> (8 * p) & 255u));
+                atomicAdd(&sm_stat[ST_RANK + p], (int)(acc.c >> (8 * p) & 255u));
+            }
+        }
     }
 }
 
@@ -128,13 +148,13 @@ __device__ __forceinline__ void ttt_zero_out(TTTOut &o) {
     o.reward = o.terminal = o.error = o.placed = o.winners = o.nvalid = 0; o.valid_after = 0;
 }
 
+template <int NP>
 __global__ void __launch_bounds__(256)
 ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int8_t *__restrict__ actions,
                 uint32_t *__restrict__ result, uint32_t *__restrict__ valid_after, crl_u64 *stats, long long B,
-                TTTParams prm, int flags) {
+                int flags) {
     __shared__ int sm_stat[CRL_NSTAT];
-    BlockStats bs{sm_stat};
-    if (stats) bs.init();
+    if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = e < B;
     TTTOut o;
@@ -144,72 +164,92 @@ ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int
     if (valid) {
         TTTEnv s;
         ttt_decode(s, ld_stream(in + e));
-        if ((flags & CRL_FLAG_AUTO_RESET) && ttt_is_terminal(s, prm)) ttt_new_state(s);
+        if ((flags & CRL_FLAG_AUTO_RESET) && ttt_is_terminal<NP>(s)) ttt_new_state(s);
         mover = s.mover;
-        ttt_step_env(s, (int)actions[e], prm, o);
+        ttt_step_env<NP>(s, (int)actions[e], o);
         ep_len = s.ep_len;
         st_stream(out + e, ttt_encode(s));
-        result[e] = ttt_pack_result(o, prm);
+        result[e] = ttt_pack_result<NP>(o);
         if (valid_after) valid_after[e] = o.valid_after;
     }
     if (stats) {
-        ttt_stats(bs, valid, o, mover, ep_len, prm);
-        bs.flush(stats);
+        TTTStatAcc acc;
+        ttt_stats<NP>(acc, valid, o, mover, ep_len);
+        ttt_stats_commit(sm_stat, acc);
+        __syncthreads();
+        stats_flush_row(sm_stat, stats);
     }
 }
 
-// k-th (0-based) set bit of a mask
+// k-th (0-based) set bit of a <= 27-bit mask: branch-free binary search on popcounts
 __device__ __forceinline__ int ttt_kth_bit(uint32_t mask, int k) {
-    for (int i = 0; i < k; i++) mask &= mask - 1;
-    return __ffs((int)mask) - 1;
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const int c = __popc(mask & ((1u << w) - 1u));
+        const bool up = k >= c;
+        k -= up ? c : 0;
+        pos += up ? w : 0;
+        mask = up ? (mask >> w) : mask;
+    }
+    return pos;
 }
 
 // uniform random policy: the (r0 % n_empty)-th empty cell in C order, pass (-1) if the board is full
-__device__ __forceinline__ int ttt_random_action(const TTTEnv &s, const TTTParams &prm, uint32_t r0) {
-    uint32_t empty = ~(s.m[0] | s.m[1] | s.m[2] | s.m[3]) & prm.cellmask;
+template <int NP>
+__device__ __forceinline__ int ttt_random_action(const TTTEnv &s, uint32_t r0) {
+    uint32_t empty = ~(s.m[0] | s.m[1] | s.m[2] | s.m[3]) & TTTGeo<NP>::CELLMASK;
     int n = __popc(empty);
     return n ? ttt_kth_bit(empty, (int)(r0 % (uint32_t)n)) : -1;
 }
 
+template <int NP>
 __global__ void ttt_policy_random_kernel(const uint4 *__restrict__ st, int8_t *__restrict__ actions, long long B,
-                                         TTTParams prm, int flags, crl_u64 seed, crl_u64 first_env, uint32_t step) {
+                                         int flags, crl_u64 seed, crl_u64 first_env, uint32_t step) {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B) return;
     TTTEnv s;
     ttt_decode(s, st[e]);
-    if ((flags & CRL_FLAG_AUTO_RESET) && ttt_is_terminal(s, prm)) ttt_new_state(s);
+    if ((flags & CRL_FLAG_AUTO_RESET) && ttt_is_terminal<NP>(s)) ttt_new_state(s);
     uint4 r = env_words(seed, first_env + (crl_u64)e, step, CRL_TAG_TTT);
-    actions[e] = (int8_t)ttt_random_action(s, prm, r.x);
+    actions[e] = (int8_t)ttt_random_action<NP>(s, r.x);
 }
 
+template <int NP>
 __global__ void __launch_bounds__(256)
 ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl_u64 *stats, long long B,
-                   TTTParams prm, crl_u64 seed, crl_u64 first_env, uint32_t step0, int K) {
+                   crl_u64 seed, crl_u64 first_env, uint32_t step0, int K) {
     __shared__ int sm_stat[CRL_NSTAT];
-    BlockStats bs{sm_stat};
-    if (stats) bs.init();
+    if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = e < B;
     TTTEnv s;
     TTTOut o;
     ttt_zero_out(o);
     ttt_new_state(s);
-    if (valid) ttt_decode(s, state[e]);
+    if (valid) ttt_decode(s, ld_stream(state + e));
     for (int k = 0; k < K; k++) {
         int mover = 0;
         if (valid) {
-            if (ttt_is_terminal(s, prm)) ttt_new_state(s);
+            if (ttt_is_terminal<NP>(s)) ttt_new_state(s);
             uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TTT);
             mover = s.mover;
-            ttt_step_env(s, ttt_random_action(s, prm, r.x), prm, o);
+            ttt_step_env<NP>(s, ttt_random_action<NP>(s, r.x), o);
         }
-        if (stats) ttt_stats(bs, valid, o, mover, s.ep_len, prm);
+        if (stats) {
+            TTTStatAcc acc;
+            ttt_stats<NP>(acc, valid, o, mover, s.ep_len);
+            ttt_stats_commit(sm_stat, acc);
+        }
     }
     if (valid) {
-        state[e] = ttt_encode(s);
-        if (result) result[e] = ttt_pack_result(o, prm);
+        st_stream(state + e, ttt_encode(s));
+        if (result) result[e] = ttt_pack_result<NP>(o);
     }
-    if (stats) bs.flush(stats);
+    if (stats) {
+        __syncthreads();
+        stats_flush_row(sm_stat, stats);
+    }
 }
 
 __global__ void ttt_reset_kernel(uint4 *__restrict__ state, const uint8_t *__restrict__ mask, long long B) {
