@@ -172,6 +172,8 @@ int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, 
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
+    static const int dbg = getenv("CRL_TRON_DEBUG_FLAGS") ? atoi(getenv("CRL_TRON_DEBUG_FLAGS")) : 0;   // diagnostics only
+    flags |= dbg;
     static const bool use_pdl = getenv("CRL_PDL") != nullptr;   // diagnostics only: PDL measured slower
     if (!use_pdl)
         CRL_LAUNCH(tron_step_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (const uint4 *)state_in,

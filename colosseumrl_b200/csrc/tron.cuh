@@ -325,7 +325,7 @@ tron_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const ui
         int act[4];
 #pragma unroll
         for (int p = 0; p < 4; p++) act[p] = (int)(int8_t)(a >> (8 * p));
-        tron_step_env(tile, t, s, act, prm, o);
+        if (!(flags & 0x100)) tron_step_env(tile, t, s, act, prm, o);     // 0x100: diagnostics (tools/): data movement only
         ep_len = s.ep_len;
         tile.v[12][t] = tron_hdr_encode(s);
         result[e0 + t] = tron_pack_result(o);

@@ -188,3 +188,49 @@ def case_reset_and_capacity(be):
     fresh = be.download(st)
     assert (after[mask == 1] == fresh[mask == 1]).all() and (after[mask == 0] == before[mask == 0]).all()
     assert be.lib.crl_blokus_legal(be.ptr(st), 4, be.ptr(st), be.ptr(st), 10, None, B, 0, be.stream) == 1
+
+
+def case_random_boards(be, n=96, seed=11):
+    """Hand-built (not necessarily reachable) positions: random colour blobs, random inventories, random round and
+    mover.  valid_actions for every seat and next_state of a random legal / pass action vs the oracle."""
+    rng = np.random.RandomState(seed)
+    boards = np.zeros((n, 20, 20), np.int8)
+    inv = (rng.rand(n, 4, 21) < rng.uniform(0.1, 0.9, size=(n, 1, 1))).astype(np.uint8)
+    scores = rng.randint(0, 90, size=(n, 4))
+    rounds = rng.randint(0, 4, size=n)
+    movers = rng.randint(0, 4, size=n)
+    for i in range(n):
+        density = rng.uniform(0.05, 0.7)
+        for _ in range(int(density * 60)):
+            c = rng.randint(1, 5)
+            y, x = rng.randint(0, 20, size=2)
+            h, w = rng.randint(1, 4, size=2)
+            if rng.rand() < 0.5:
+                boards[i, y:y + h, x:x + w] = np.where(boards[i, y:y + h, x:x + w] == 0, c, boards[i, y:y + h, x:x + w])
+            else:
+                boards[i, y, x] = c
+        if i % 7 == 0:
+            boards[i] = 0          # empty boards with odd inventories / rounds
+    st = blk_pack(be, boards, inv, scores, rounds, movers)
+    lists = {}
+    for p in range(4):
+        counts, ids = blk_legal(be, st, player=p, cap=4096)
+        for i in range(n):
+            exp = orc.blokus_valid_moves((boards[i].astype(np.int64), int(rounds[i]), inv[i], scores[i]), p, cap=16384)
+            assert counts[i] == len(exp), (i, p, counts[i], len(exp))
+            assert (ids[i, :len(exp)] == exp).all(), (i, p)
+            lists[(i, p)] = exp
+    acts = np.full(n, -1, np.int32)
+    for i in range(n):
+        v = lists[(i, int(movers[i]))]
+        if len(v) and i % 5 != 0:
+            acts[i] = v[rng.randint(len(v))]
+    out, r = blk_step(be, st, acts)
+    b2, p2, s2, m2 = blk_unpack(be, out)
+    for i in range(n):
+        ost = (boards[i].astype(np.int64), int(rounds[i]), inv[i], scores[i].astype(np.int64))
+        nst, nxt, rew, term, win = orc.blokus_next_state(ost, int(movers[i]), int(acts[i]))
+        assert (b2[i] == nst[0]).all() and (p2[i] == nst[2]).all() and (s2[i] == nst[3]).all(), i
+        assert m2[i, 0] == nst[1] and m2[i, 1] == nxt and bool(m2[i, 2]) == term
+        assert r["reward"][i] == rew and r["terminal"][i] == term and r["winners"][i] == (win if term else 0), i
+        assert not r["error"][i]

@@ -31,3 +31,7 @@ def test_rollout_vs_oracle(be):
 def test_rollout_vs_oracle_wide(be):
     # many games, two+ full episodes each: end states and fused statistics bit-exact vs the oracle
     cases.case_rollout_vs_oracle(be, B=1024, K=150, seed=0, env0=0)
+
+
+def test_random_boards(be):
+    cases.case_random_boards(be, n=160)

@@ -23,4 +23,8 @@ def test_illegal_actions(be):
 
 
 def test_rollout_vs_oracle(be):
-    cases.case_rollout_vs_oracle(be, B=8, K=76)
+    cases.case_rollout_vs_oracle(be, B=4, K=72)
+
+
+def test_random_boards(be):
+    cases.case_random_boards(be, n=20)

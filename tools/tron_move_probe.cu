@@ -3,6 +3,7 @@
 // Same harness as bench.py: G replicas (> 4 x L2), in-place, K launches captured in one CUDA graph.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/tron_move_probe tools/tron_move_probe.cu
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <cstdio>
 #include <cstdint>
 #include <vector>
@@ -115,6 +116,92 @@ __global__ void __launch_bounds__(TILE) k_tma_persist(uint4 *st, long long B, in
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// V3: ONE 2-D tensor-map TMA load and ONE store per CTA (box = TILE*4 uint32 x 13 rows of the [13][B*4] tensor)
+template <int TILE, int WARPS>
+__global__ void __launch_bounds__(TILE) k_tma2d(const __grid_constant__ CUtensorMap tm, long long B) {
+    __shared__ __align__(128) uint4 tile[13][TILE];
+    __shared__ __align__(8) uint64_t bar;
+    const int x0 = (int)(blockIdx.x * TILE * 4);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar)), "r"(13 * TILE * 16) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     :: "r"(smem_u32(&tile[0][0])), "l"(&tm), "r"(x0), "r"(0), "r"(smem_u32(&bar)) : "memory");
+    }
+    __syncthreads();
+    asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" :: "r"(smem_u32(&bar)) : "memory");
+    uint4 h = tile[12][threadIdx.x];
+    h.x ^= tile[threadIdx.x % 12][threadIdx.x].y;
+    tile[12][threadIdx.x] = h;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                     :: "l"(&tm), "r"(x0), "r"(0), "r"(smem_u32(&tile[0][0])) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// V4: like V1 but the 13 bulk copies are issued by 13 different warps' ... (TILE threads = TILE/32 warps): warp w issues v = w, w+W, ...
+template <int TILE>
+__global__ void __launch_bounds__(TILE) k_tma_split(uint4 *st, long long B) {
+    __shared__ __align__(128) uint4 tile[13][TILE];
+    __shared__ __align__(8) uint64_t bar;
+    constexpr int W = TILE / 32;
+    const long long e0 = (long long)blockIdx.x * TILE;
+    const int w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar)), "r"(W));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        int nv = 0;
+        for (int v = w; v < 13; v += W) nv++;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar)), "r"(nv * TILE * 16) : "memory");
+        for (int v = w; v < 13; v += W)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(&tile[v][0])), "l"(st + (long long)v * B + e0), "r"(TILE * 16), "r"(smem_u32(&bar)) : "memory");
+    }
+    asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" :: "r"(smem_u32(&bar)) : "memory");
+    uint4 h = tile[12][threadIdx.x];
+    h.x ^= tile[threadIdx.x % 12][threadIdx.x].y;
+    tile[12][threadIdx.x] = h;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        for (int v = w; v < 13; v += W)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(st + (long long)v * B + e0), "r"(smem_u32(&tile[v][0])), "r"(TILE * 16) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_fn get_encode() {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    return (encode_fn)fn;
+}
+template <int TILE>
+static CUtensorMap make_map(uint4 *p, long long B) {
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {(cuuint64_t)B * 4, 13};
+    cuuint64_t strides[1] = {(cuuint64_t)B * 16};
+    cuuint32_t box[2] = {TILE * 4, 13};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed %d\n", (int)r); exit(1); }
+    return tm;
+}
+
 struct Harness {
     long long B; int G, K;
     std::vector<uint4 *> rep;
@@ -172,22 +259,22 @@ int main(int argc, char **argv) {
     int K = argc > 2 ? atoi(argv[2]) : 400;
     Harness h(B, K);
     printf("B = %lld envs, %d replicas, %d launches per graph\n", B, h.G, K);
-    h.run("ldg/stg 128-bit, block 64, no work", [&](uint4 *p, cudaStream_t s) { k_ldg<64, 0><<<(unsigned)((B + 63) / 64), 64, 0, s>>>(p, B); });
-    h.run("ldg/stg 128-bit, block 128, no work", [&](uint4 *p, cudaStream_t s) { k_ldg<128, 0><<<(unsigned)((B + 127) / 128), 128, 0, s>>>(p, B); });
-    h.run("ldg/stg 128-bit, block 256, no work", [&](uint4 *p, cudaStream_t s) { k_ldg<256, 0><<<(unsigned)((B + 255) / 256), 256, 0, s>>>(p, B); });
-    h.run("ldg/stg 128-bit, block 128, 400 instr", [&](uint4 *p, cudaStream_t s) { k_ldg<128, 200><<<(unsigned)((B + 127) / 128), 128, 0, s>>>(p, B); });
     h.run("tma tile 32, no work", [&](uint4 *p, cudaStream_t s) { launch_tma<32, 0, false>(p, B, s); });
     h.run("tma tile 64, no work", [&](uint4 *p, cudaStream_t s) { launch_tma<64, 0, false>(p, B, s); });
     h.run("tma tile 128, no work", [&](uint4 *p, cudaStream_t s) { launch_tma<128, 0, false>(p, B, s); });
-    h.run("tma tile 64, 400 instr", [&](uint4 *p, cudaStream_t s) { launch_tma<64, 200, false>(p, B, s); });
-    h.run("tma tile 64, 1000 instr", [&](uint4 *p, cudaStream_t s) { launch_tma<64, 500, false>(p, B, s); });
-    h.run("tma tile 128, 400 instr", [&](uint4 *p, cudaStream_t s) { launch_tma<128, 200, false>(p, B, s); });
     h.run("tma tile 64, no work, PDL", [&](uint4 *p, cudaStream_t s) { launch_tma<64, 0, true>(p, B, s); });
     h.run("tma tile 128, no work, PDL", [&](uint4 *p, cudaStream_t s) { launch_tma<128, 0, true>(p, B, s); });
-    h.run("tma tile 64, 400 instr, PDL", [&](uint4 *p, cudaStream_t s) { launch_tma<64, 200, true>(p, B, s); });
+    {
+        std::vector<CUtensorMap> maps64, maps32;
+        for (auto p : h.rep) { maps64.push_back(make_map<64>(p, B)); maps32.push_back(make_map<32>(p, B)); }
+        auto idx = [&](uint4 *p) { return (int)(std::find(h.rep.begin(), h.rep.end(), p) - h.rep.begin()); };
+        h.run("tma 2-D tensor map, tile 64 (1 load + 1 store)", [&](uint4 *p, cudaStream_t s) { k_tma2d<64, 2><<<(unsigned)(B / 64), 64, 0, s>>>(maps64[idx(p)], B); });
+        h.run("tma 2-D tensor map, tile 32 (1 load + 1 store)", [&](uint4 *p, cudaStream_t s) { k_tma2d<32, 1><<<(unsigned)(B / 32), 32, 0, s>>>(maps32[idx(p)], B); });
+    }
+    h.run("tma tile 64, copies issued by 2 warps", [&](uint4 *p, cudaStream_t s) { k_tma_split<64><<<(unsigned)(B / 64), 64, 0, s>>>(p, B); });
+    h.run("tma tile 128, copies issued by 4 warps", [&](uint4 *p, cudaStream_t s) { k_tma_split<128><<<(unsigned)(B / 128), 128, 0, s>>>(p, B); });
     h.run("persistent 148x1, tile 64, 4 stages", [&](uint4 *p, cudaStream_t s) { launch_persist<64, 4, 0>(p, B, s, 1); });
     h.run("persistent 148x2, tile 64, 3 stages", [&](uint4 *p, cudaStream_t s) { launch_persist<64, 3, 0>(p, B, s, 2); });
     h.run("persistent 148x4, tile 32, 2 stages", [&](uint4 *p, cudaStream_t s) { launch_persist<32, 2, 0>(p, B, s, 4); });
-    h.run("persistent 148x2, tile 64, 3 st, 400 instr", [&](uint4 *p, cudaStream_t s) { launch_persist<64, 3, 200>(p, B, s, 2); });
     return 0;
 }
