@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcolosseum_b200.so")
 
 NSTAT = 32
-STAT_ROWS = 16
+STAT_ROWS = 256
 FLAG_AUTO_RESET = 1
 
 _vp, _i64, _i32, _u64, _u32, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, C.c_int

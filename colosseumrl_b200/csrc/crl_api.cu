@@ -127,17 +127,66 @@ static int tron_params(int N, int P, TronParams &prm) {
     int32_t heads[4] = {0, 0, 0, 0}, dirs[4] = {0, 0, 0, 0};
     if (tron_starts(N, P, heads, dirs) != CRL_OK) return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N/P%s");
     prm.N = N; prm.P = P;
+    prm.pmask = 0; prm.rkmask = (1u << (2 * P)) - 1u;
     TronHdr h;
     for (int p = 0; p < 4; p++) {
+        if (p < P) prm.pmask |= 1u << (8 * p);
         h.hx[p] = p < P ? heads[p] % N : 0; h.hy[p] = p < P ? heads[p] / N : 0;
         h.dir[p] = p < P ? dirs[p] : 0; h.death[p] = 0; h.cells[p] = p < P ? 1 : 0;
-        for (int w = 0; w < TRON_WORDS; w++)
-            prm.start_pl[p][w] = (p < P && (heads[p] >> 6) == w) ? 1ull << (heads[p] & 63) : 0ull;
+        prm.spawn_word[p] = p < P ? (uint32_t)(heads[p] >> 5) : 0u;
+        prm.spawn_bit[p] = p < P ? 1u << (heads[p] & 31) : 0u;
     }
     h.terminal = 0; h.ep_len = 0;
     uint4 e = tron_hdr_encode(h);
     prm.start_hdr[0] = e.x; prm.start_hdr[1] = e.y; prm.start_hdr[2] = e.z; prm.start_hdr[3] = e.w;
     return CRL_OK;
+}
+
+// Tensor map of the plane part of a Tron state buffer: [12 rows][B*4 uint32], row pitch B*16 bytes, box = 12 rows x
+// tile*4 words.  The driver's encoder is fetched through the runtime (no link-time dependency on libcuda); the last
+// few maps are cached per thread because an actor steps the same buffers over and over.
+#ifndef CRL_HOSTSIM
+typedef CUresult (*crl_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int tron_plane_map(const void *state, int64_t B, int tile, CUtensorMap *out) {
+    struct Entry { const void *p; int64_t B; int tile; CUtensorMap tm; };
+    static thread_local Entry cache[8];
+    static thread_local int next = 0;
+    for (int i = 0; i < 8; i++)
+        if (cache[i].p == state && cache[i].B == B && cache[i].tile == tile) { *out = cache[i].tm; return CRL_OK; }
+    static crl_encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            return fail(CRL_ERR_CUDA, "cuTensorMapEncodeTiled is not available%s");
+        encode = (crl_encode_fn)fn;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)B * 4, 12};
+    cuuint64_t strides[1] = {(cuuint64_t)B * 16};
+    cuuint32_t box[2] = {(cuuint32_t)tile * 4, 12};
+    cuuint32_t estr[2] = {1, 1};
+    Entry &e = cache[next];
+    CUresult r = encode(&e.tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(state), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { e.p = nullptr; return fail(CRL_ERR_CUDA, "cuTensorMapEncodeTiled failed%s"); }
+    e.p = state; e.B = B; e.tile = tile;
+    *out = e.tm;
+    next = (next + 1) & 7;
+    return CRL_OK;
+}
+#endif
+
+// environments (= threads) per CTA of the step / rollout kernels: 64 (13 KB of shared memory, ~7 CTAs per SM at
+// B = 65,536); CRL_TRON_TILE=32 for exploration
+static int tron_tile() {
+    static const int tile = [] {
+        const int t = getenv("CRL_TRON_TILE") ? atoi(getenv("CRL_TRON_TILE")) : 64;
+        return t == 32 ? 32 : 64;
+    }();
+    return tile;
 }
 
 int64_t crl_tron_state_bytes(int N, int P, int64_t B) {
@@ -172,15 +221,31 @@ int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, 
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
-    static const int dbg = getenv("CRL_TRON_DEBUG_FLAGS") ? atoi(getenv("CRL_TRON_DEBUG_FLAGS")) : 0;   // diagnostics only
-    flags |= dbg;
-    static const bool use_pdl = getenv("CRL_PDL") != nullptr;   // diagnostics only: PDL measured slower
-    if (!use_pdl)
-        CRL_LAUNCH(tron_step_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (const uint4 *)state_in,
-                   (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags);
-    else
-        CRL_LAUNCH_PDL(tron_step_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (const uint4 *)state_in,
-                       (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags);
+    if (((uintptr_t)state_in | (uintptr_t)state_out) & 15) return fail(CRL_ERR_ARG, "crl_tron_step: state buffers must be 16-byte aligned%s");
+    if (B > (INT32_MAX >> 2)) return fail(CRL_ERR_UNSUPPORTED, "crl_tron_step: batch too large for one launch%s");
+    const int tile = tron_tile();
+    TronMaps maps;
+#ifndef CRL_HOSTSIM
+    if ((rc = tron_plane_map(state_in, B, tile, &maps.in))) return rc;
+    if ((rc = tron_plane_map(state_out, B, tile, &maps.out))) return rc;
+#else
+    maps.unused = 0;
+#endif
+    // Programmatic dependent launch: the kernel waits (griddepcontrol.wait) for its predecessor's completion before
+    // it touches memory, and lets its successor's CTAs become resident once its own planes are on their way back.
+    // Only launches carrying the attribute may start early, so ordering against any other kernel is unchanged.
+    static const bool use_pdl = !(getenv("CRL_PDL") && atoi(getenv("CRL_PDL")) == 0);
+#define TRON_STEP_ARGS maps, (const uint4 *)state_in, (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, \
+                       (crl_u64 *)stats, (long long)B, prm, flags
+#define TRON_STEP_LAUNCH(T)                                                                                         \
+    do {                                                                                                          \
+        if (use_pdl) CRL_LAUNCH_PDL(tron_step_kernel<T>, blocks_for(B, T), T, (cudaStream_t)stream, TRON_STEP_ARGS);   \
+        else CRL_LAUNCH(tron_step_kernel<T>, blocks_for(B, T), T, (cudaStream_t)stream, TRON_STEP_ARGS);              \
+    } while (0)
+    if (tile == 32) TRON_STEP_LAUNCH(32);
+    else TRON_STEP_LAUNCH(64);
+#undef TRON_STEP_LAUNCH
+#undef TRON_STEP_ARGS
     return check_launch("tron_step_kernel");
 }
 
@@ -201,8 +266,12 @@ int crl_tron_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0 || K == 0) return CRL_OK;
-    CRL_LAUNCH(tron_rollout_kernel, blocks_for(B, TRON_TILE), TRON_TILE, (cudaStream_t)stream, (uint4 *)state, (uint2 *)result,
-               (crl_u64 *)stats, (long long)B, prm, (crl_u64)seed, (crl_u64)first_env, step0, K);
+    if (tron_tile() == 32)
+        CRL_LAUNCH(tron_rollout_kernel<32>, blocks_for(B, 32), 32, (cudaStream_t)stream, (uint4 *)state, (uint2 *)result,
+                   (crl_u64 *)stats, (long long)B, prm, (crl_u64)seed, (crl_u64)first_env, step0, K);
+    else
+        CRL_LAUNCH(tron_rollout_kernel<64>, blocks_for(B, 64), 64, (cudaStream_t)stream, (uint4 *)state, (uint2 *)result,
+                   (crl_u64 *)stats, (long long)B, prm, (crl_u64)seed, (crl_u64)first_env, step0, K);
     return check_launch("tron_rollout_kernel");
 }
 

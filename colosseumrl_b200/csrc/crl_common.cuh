@@ -4,6 +4,7 @@
 
 #ifndef CRL_HOSTSIM
 #include <cuda_runtime.h>
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
 #define CRL_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 // launch with the programmatic-stream-serialization attribute (PDL); the kernel must call pdl_wait() before it
 // touches memory written by its predecessor in the stream
@@ -26,8 +27,8 @@
 #endif
 
 #define CRL_NSTAT 32
-#define CRL_STAT_ROWS 16   // the device statistics buffer is int64[CRL_STAT_ROWS][CRL_NSTAT]; CTAs spread their
-                           // partial sums over the rows (row = blockIdx % 16) so same-address L2 atomics do not
+#define CRL_STAT_ROWS 256  // the device statistics buffer is int64[CRL_STAT_ROWS][CRL_NSTAT]; CTAs spread their
+                           // partial sums over the rows (row = blockIdx % 256) so same-address L2 atomics do not
                            // serialise; the reader sums the rows
 // statistics slots (int64 each); identical to oracle/oracle_rollout.c
 enum {
@@ -90,6 +91,18 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
+// 2-D tiled TMA through a tensor map (SASS UTMALDG / UTMASTG): ONE instruction moves a whole [rows][TILE*16 B] box,
+// out-of-range columns are zero-filled on loads and clipped on stores
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *tm, int x, int y, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(dst_smem)), "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int x, int y, const void *src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(tm), "r"(x), "r"(y), "r"(smem_u32(src_smem)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

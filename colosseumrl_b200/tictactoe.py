@@ -69,11 +69,11 @@ class _BatchedTicTacToe(BatchedBaseEnvironment):
                                            self.batch, self.N_PLAYERS, self.flags, self._stream))
         return new
 
-    def host_stepper(self, state: TTTBatchState):
+    def host_stepper(self, state: TTTBatchState, stream=None):
         """Graph-fused H2D actions -> step -> D2H result for host-side policies (see base.HostStepper).
         NOTE: the warm-up inside applies one step of cell-0 actions to `state`."""
         from .base import HostStepper
-        return HostStepper(self, state, (self.batch,), torch.int8)
+        return HostStepper(self, state, (self.batch,), torch.int8, stream=stream)
 
     def valid_actions(self, state: TTTBatchState, player=None) -> torch.Tensor:
         """valid_actions (2p :317-348) as a bit mask: int32 [B], bit c = cell c (C order) is empty; 0 <=> ['']."""

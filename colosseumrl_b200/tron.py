@@ -101,11 +101,11 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
                                             self.num_players, self.flags, self._stream))
         return new
 
-    def host_stepper(self, state: TronBatchState):
+    def host_stepper(self, state: TronBatchState, stream=None):
         """Graph-fused H2D actions -> step -> D2H result for host-side policies (see base.HostStepper).
         NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
         from .base import HostStepper
-        return HostStepper(self, state, (self.batch, 4), torch.int8)
+        return HostStepper(self, state, (self.batch, 4), torch.int8, stream=stream)
 
     def valid_actions(self, state, player):
         """Always ['forward', 'right', 'left'] (:325-341): uint8 [B, 3] of ones."""
@@ -117,7 +117,7 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
     def is_terminal(self, state: TronBatchState) -> torch.Tensor:
         if state.result is not None:
             return state.result[:, 4]
-        return ((state.packed[12, :, 1] >> 30) & 1).to(torch.uint8)
+        return ((state.packed[12, :, 2] >> 27) & 1).to(torch.uint8)
 
     def compute_ranking(self, state: TronBatchState, players=None, winners=None) -> torch.Tensor:
         """TronGridEnvironment.compute_ranking (:483-508), fused into the step: uint8 [B, P]."""

@@ -35,7 +35,7 @@ extern "C" {
  * CTAs spread their partial sums over the rows so that same-address L2 atomics do not serialise; the value of
  * slot s is the sum over rows of stats[row][s]. */
 #define CRL_NSTAT 32
-#define CRL_STAT_ROWS 16
+#define CRL_STAT_ROWS 256
 #define CRL_ST_STEPS 0     /* env-steps                                   */
 #define CRL_ST_EPISODES 1  /* finished episodes (terminal transitions)    */
 #define CRL_ST_EPLEN 2     /* sum of finished-episode lengths             */

@@ -4,6 +4,7 @@ import os
 import numpy as np
 
 from oracle import oracle as orc
+from colosseumrl_b200._lib import STAT_ROWS
 from colosseumrl_b200 import philox
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -145,7 +146,7 @@ def case_rollout_vs_oracle(be, B=24, K=80, seed=3, env0=500, cap=2048):
     ob = orc.BlokusBatch(B)
     ob.rollout(seed, env0, 0, K, fresh=True)
     st, st2 = be.zeros((B, 22, 4), np.int32), be.zeros((B, 22, 4), np.int32)
-    stats = be.zeros((16, 32), np.int64)
+    stats = be.zeros((STAT_ROWS, 32), np.int64)
     counts, ids = be.zeros((B,), np.int32), be.zeros((B, cap), np.int32)
     act, res = be.zeros((B,), np.int32), be.zeros((B, 8), np.uint8)
     be.check(be.lib.crl_blokus_reset(be.ptr(st), None, B, be.stream))

@@ -5,6 +5,7 @@ import os
 import numpy as np
 
 from oracle import oracle as orc
+from colosseumrl_b200._lib import STAT_ROWS
 from colosseumrl_b200 import philox
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -134,7 +135,7 @@ def case_rollout_vs_oracle(be, N=19, P=4, B=200, K=48, seed=5, env0=1000):
     ob.rollout(seed, env0, 0, K, fresh=True)
     st = be.zeros((13, B, 4), np.int32)
     st2 = be.zeros((13, B, 4), np.int32)
-    stats = be.zeros((16, 32), np.int64)
+    stats = be.zeros((STAT_ROWS, 32), np.int64)
     act = be.zeros((B, 4), np.int8)
     res = be.zeros((B, 8), np.uint8)
     be.check(be.lib.crl_tron_reset(be.ptr(st), None, B, N, P, be.stream))
@@ -154,7 +155,7 @@ def case_rollout_vs_oracle(be, N=19, P=4, B=200, K=48, seed=5, env0=1000):
     assert (s == ob.stats).all(), (s, ob.stats)
     # fused K-step kernel, split in two launches
     st3 = be.zeros((13, B, 4), np.int32)
-    stats3 = be.zeros((16, 32), np.int64)
+    stats3 = be.zeros((STAT_ROWS, 32), np.int64)
     be.check(be.lib.crl_tron_reset(be.ptr(st3), None, B, N, P, be.stream))
     be.check(be.lib.crl_tron_rollout(be.ptr(st3), None, be.ptr(stats3), seed, env0, 0, K // 3, B, N, P, be.stream))
     be.check(be.lib.crl_tron_rollout(be.ptr(st3), be.ptr(res), be.ptr(stats3), seed, env0, K // 3, K - K // 3, B, N, P, be.stream))

@@ -5,6 +5,7 @@ import os
 import numpy as np
 
 from oracle import oracle as orc
+from colosseumrl_b200._lib import STAT_ROWS
 from colosseumrl_b200 import philox
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -80,7 +81,7 @@ def case_rollout_vs_oracle(be, n, B=300, K=40, seed=4, env0=77):
     ob = orc.TTTBatch(B, n)
     ob.rollout(seed, env0, 0, K, fresh=True)
     st, st2 = be.zeros((B, 4), np.int32), be.zeros((B, 4), np.int32)
-    stats = be.zeros((16, 32), np.int64)
+    stats = be.zeros((STAT_ROWS, 32), np.int64)
     act, res = be.zeros((B,), np.int8), be.zeros((B, 4), np.uint8)
     be.check(be.lib.crl_ttt_reset(be.ptr(st), None, B, n, be.stream))
     cur, nxt = st, st2
@@ -94,7 +95,7 @@ def case_rollout_vs_oracle(be, n, B=300, K=40, seed=4, env0=77):
     assert (s == ob.stats).all(), (s, ob.stats)
     term = unpack_result(be.download(res))["terminal"]
     assert (term == ob.terminal.astype(bool)).all()
-    st3, stats3 = be.zeros((B, 4), np.int32), be.zeros((16, 32), np.int64)
+    st3, stats3 = be.zeros((B, 4), np.int32), be.zeros((STAT_ROWS, 32), np.int64)
     be.check(be.lib.crl_ttt_reset(be.ptr(st3), None, B, n, be.stream))
     be.check(be.lib.crl_ttt_rollout(be.ptr(st3), None, be.ptr(stats3), seed, env0, 0, 7, B, n, be.stream))
     be.check(be.lib.crl_ttt_rollout(be.ptr(st3), be.ptr(res), be.ptr(stats3), seed, env0, 7, K - 7, B, n, be.stream))

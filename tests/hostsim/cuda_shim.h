@@ -21,6 +21,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __shared__ static
 #define __constant__ static const
 #define __align__(n) __attribute__((aligned(n)))
@@ -145,6 +146,20 @@ static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
     for (unsigned i = base; i < 32; i++)
         if ((mask >> i) & 1u) { if (--offset == 0) return i; }
     return 0xffffffffu;
+}
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {   // PRMT, default mode (incl. sign replication)
+    uint64_t ab = ((uint64_t)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned n = (s >> (4 * i)) & 15u, byte = (unsigned)(ab >> (8 * (n & 7u))) & 255u;
+        if (n & 8u) byte = (byte & 0x80u) ? 0xFFu : 0u;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __vminu2(unsigned a, unsigned b) {
+    unsigned al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16, lo = al < bl ? al : bl, hi = ah < bh ? ah : bh;
+    return lo | hi << 16;
 }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
