@@ -103,13 +103,8 @@ class ClockSampler:
 def graph_upload(graph, stream):
     """cudaGraphUpload of a captured torch graph: without it the first replay pays for moving the executable graph to
     the device inside the timed region.  (No kernel runs here; the K timed steps are the graph's only execution.)"""
-    import ctypes
-    rt = ctypes.CDLL("libcudart.so.12")
-    rt.cudaGraphUpload.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-    rt.cudaGraphUpload.restype = ctypes.c_int
-    rc = rt.cudaGraphUpload(ctypes.c_void_p(graph.raw_cuda_graph_exec()), ctypes.c_void_p(stream.cuda_stream))
-    if rc != 0:
-        raise RuntimeError("cudaGraphUpload failed: %d" % rc)
+    from colosseumrl_b200 import _cudart
+    _cudart.check(_cudart.rt().cudaGraphUpload(graph.raw_cuda_graph_exec(), stream.cuda_stream), "cudaGraphUpload")
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
@@ -174,7 +169,7 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- GPU workloads
-E2E_DEPTH = 4       # environment batches an actor keeps in flight (one CUDA stream each)
+E2E_DEPTH = 8       # environment batches an actor keeps in flight (one CUDA stream each)
 
 
 def _pipelined_e2e_step(work, k, probe_col):
@@ -477,8 +472,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stats", action="store_true", help="exploration: skip the fused episode statistics")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (exploration only)")
+    ap.add_argument("--e2e-depth", type=int, default=0, help="environment batches in flight in the e2e leg (0 = default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.e2e_depth > 0:
+        global E2E_DEPTH
+        E2E_DEPTH = args.e2e_depth
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -55,22 +55,34 @@ class HostStepper:
             env.step_(state, self._dev_actions, out=state)
             self.result.copy_(state.result, non_blocking=True)
 
-        self._done = torch.cuda.Event()
+        # replay / completion through the CUDA runtime directly: three ctypes calls per step instead of torch's
+        # stream context + event objects (the host loop is CPU-bound)
+        from . import _cudart
+        self._rt = _cudart.rt()
+        self._exec = self.graph.raw_cuda_graph_exec()
+        self._done = _cudart.new_event()
+        s = stream if stream is not None else torch.cuda.current_stream(env.device)
+        self._stream_handle = s.cuda_stream
+        _cudart.check(self._rt.cudaGraphUpload(self._exec, self._stream_handle), "cudaGraphUpload")
 
     def launch(self):
         """Enqueue H2D + step + D2H (one graph launch) on the stepper's stream; returns immediately."""
-        if self.stream is None:
-            self.graph.replay()
-            self._done.record(torch.cuda.current_stream(self.env.device))
-        else:
-            with torch.cuda.stream(self.stream):
-                self.graph.replay()
-                self._done.record(self.stream)
+        rc = self._rt.cudaGraphLaunch(self._exec, self._stream_handle) or self._rt.cudaEventRecord(self._done, self._stream_handle)
+        if rc:
+            raise RuntimeError("HostStepper launch failed: cudaError %d" % rc)
 
     def wait(self):
         """Block until the launched step's result record is in `self.result` (pinned host memory)."""
-        self._done.synchronize()
+        rc = self._rt.cudaEventSynchronize(self._done)
+        if rc:
+            raise RuntimeError("HostStepper wait failed: cudaError %d" % rc)
         return self.result
+
+    def __del__(self):
+        try:
+            self._rt.cudaEventDestroy(self._done)
+        except Exception:
+            pass
 
     def __call__(self):
         self.launch()

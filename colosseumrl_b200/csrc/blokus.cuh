@@ -24,6 +24,12 @@
 // action (piece, anchor a, orientation o, shift k) is legal  <=>  a in ANC  and  FIT_s[a - cell_k(s)],
 // s = shape(piece, o).  The list is emitted in the reference's order piece -> anchor (row-major) -> o -> k, with
 // lanes = the (o, k) ids of one piece and __ballot_sync / __popc prefix sums for the compaction.
+//
+// FIT boards: the 91 oriented shapes are exactly the fixed polyominoes of 1..5 cells, so each is a smaller one plus
+// a cell and FIT_s[q] = FIT_parent[q + off] & A[q + c]: all boards a player needs cost <= 90 AND steps (lanes = rows),
+// generated as straight-line code from blokus_tables.h (every offset an immediate).  Shapes whose pieces are not held
+// or whose parent fits nowhere are skipped.  The any-move test of the terminal check needs no anchor loop at all:
+// piece p has a move  <=>  OR_s OR_k (ANC & shift(FIT_s, cell_k)) != 0, evaluated level by level with an early exit.
 #pragma once
 #include "crl_common.cuh"
 #include "philox.cuh"
@@ -35,13 +41,20 @@
 #define BLK_ROWMASK 0xFFFFFu
 #define BLK_MAX_ANCHORS 400
 
+#define BLK_FROWS 24           // rows of a FIT board: y = -4..19 at index y + 4 (rows -4..-1 are zero)
+#define BLK_FSLOTS (BLK_NSHAPE_LE4 + 8)
+#define BLK_SLOT(s, local) ((s) < BLK_NSHAPE_LE4 ? (s) : BLK_NSHAPE_LE4 + (local))
+
 // per-warp shared scratch
 struct BlkSmem {
     uint32_t st[BLK_WORDS];          // the game state (old board during a step)
     uint32_t A[24];                  // allowed rows; rows 20..23 are zero (shapes are at most 5 rows tall)
     uint32_t anc[20];                // anchor rows
-    uint32_t F[8 * 20];              // FIT boards of the current piece's (<= 8) shapes
-    uint16_t alist[BLK_MAX_ANCHORS]; // anchors, row-major: y*20 + x
+    uint32_t F[BLK_FSLOTS * BLK_FROWS];   // FIT boards: bit (x + 4) of word [slot * 24 + y + 4]; the padding makes
+                                     // FIT_s[a - cell] a plain load + shift for every anchor a and shape cell.
+                                     // Slots 0..27: the shapes of <= 4 cells; slots 28..35: the shapes of the ONE
+                                     // pentomino piece being processed (5-cell shapes have no children)
+    uint16_t alist[BLK_MAX_ANCHORS + 4]; // anchors, row-major: y << 8 | (x + 4), then four padding entries
 };
 
 __device__ __forceinline__ void blk_load(BlkSmem &sm, const uint4 *__restrict__ st, long long g, int lane) {
@@ -97,71 +110,196 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
     while (an) {
         int x = __ffs((int)an) - 1;
         an &= an - 1;
-        sm.alist[pos++] = (uint16_t)(lane * 20 + x);
+        sm.alist[pos++] = (uint16_t)(lane << 8 | (x + 4));
     }
+    if (lane < 4) sm.alist[total + lane] = 28;       // padding: "anchors" whose column lies outside every FIT board
     __syncwarp();
     return total;
 }
 
-// FIT boards of piece p's shapes into sm.F (lanes = rows)
-__device__ __forceinline__ void blk_fit_boards(BlkSmem &sm, int p, int lane) {
-    const int s0 = BLK_PIECE_SHAPE0[p], ns = BLK_PIECE_SHAPE0[p + 1] - s0;
-    __syncwarp();
-    if (lane < 20) {
-        for (int sl = 0; sl < ns; sl++) {
-            uint32_t cells = BLK_SHAPE_CELLS[s0 + sl], f = BLK_ROWMASK;
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                uint32_t cd = cells >> (6 * i);
-                f &= sm.A[lane + ((cd >> 3) & 7)] >> (cd & 7);
-            }
-            sm.F[sl * 20 + lane] = f;
-        }
+// ---- FIT boards through the polyomino tree -----------------------------------------------------------------
+// ne = bit s set iff FIT_s (s < 28) has been built and is not empty; ne5 = the same for the 8 slots of the
+// current pentomino piece (both warp-uniform)
+
+// shape 0 (the monomino): FIT = A
+__device__ __forceinline__ uint32_t blk_tree_root(BlkSmem &sm, int lane, int frow) {
+    const uint32_t f = lane < 20 ? sm.A[lane] << 4 : 0u;
+    if (lane < BLK_FROWS) sm.F[frow] = f;
+    return __any_sync(0xffffffffu, f != 0u) ? 1u : 0u;
+}
+
+// one tree step; every argument except sm / ne / lane / frow is a literal
+#define BLK_TREE_STEP(s, local, par, px, py, cx, cy, nevar)                                                   \
+    if (ne >> (par) & 1u) {                                                                                   \
+        uint32_t f_ = 0u;                                                                                     \
+        if (lane < 20 - (py)) f_ = (sm.F[(par) * BLK_FROWS + 4 + (py) + lane] >> (px)) & ((sm.A[lane + (cy)] >> (cx)) << 4); \
+        if (lane < BLK_FROWS) sm.F[BLK_SLOT(s, local) * BLK_FROWS + frow] = f_;                                 \
+        if (__any_sync(0xffffffffu, f_ != 0u)) nevar |= 1u << ((s) < BLK_NSHAPE_LE4 ? (s) : (local));          \
     }
+
+// the shapes with LEVEL (2..4) cells that some held piece needs
+template <int LEVEL>
+__device__ __forceinline__ void blk_tree_level(BlkSmem &sm, uint32_t &ne, uint32_t inv, int lane, int frow) {
+#define BLK_X(level, s, piece, local, par, px, py, cx, cy, need) \
+    if ((level) == LEVEL && (inv & (need))) BLK_TREE_STEP(s, local, par, px, py, cx, cy, ne)
+    BLK_TREE_LIST(BLK_X)
+#undef BLK_X
     __syncwarp();
 }
 
-// Enumerate the legal moves of player c holding `inv` on the board in sm.st.
-//   EMIT = true : write action ids (canonical order) to out[0..cap) and return the full count
-//   EMIT = false: return 1 as soon as any move exists, else 0   (AI.check_moves, ai.py:36-42)
-template <bool EMIT>
+// the (<= 8) shapes of pentomino piece PIECE into slots 28..35; returns their non-empty flags
+template <int PIECE>
+__device__ __forceinline__ uint32_t blk_tree_pentomino(BlkSmem &sm, uint32_t ne, int lane, int frow) {
+    uint32_t ne5 = 0u;
+#define BLK_X(level, s, piece, local, par, px, py, cx, cy, need) \
+    if ((level) == 5 && (piece) == PIECE) BLK_TREE_STEP(s, local, par, px, py, cx, cy, ne5)
+    BLK_TREE_LIST(BLK_X)
+#undef BLK_X
+    __syncwarp();
+    return ne5;
+}
+
+__device__ __forceinline__ uint32_t blk_tree_pentomino_dyn(BlkSmem &sm, int p, uint32_t ne, int lane, int frow) {
+    __syncwarp();                // the previous piece's readers are done with slots 28..35
+    switch (p) {
+    case 9: return blk_tree_pentomino<9>(sm, ne, lane, frow);
+    case 10: return blk_tree_pentomino<10>(sm, ne, lane, frow);
+    case 11: return blk_tree_pentomino<11>(sm, ne, lane, frow);
+    case 12: return blk_tree_pentomino<12>(sm, ne, lane, frow);
+    case 13: return blk_tree_pentomino<13>(sm, ne, lane, frow);
+    case 14: return blk_tree_pentomino<14>(sm, ne, lane, frow);
+    case 15: return blk_tree_pentomino<15>(sm, ne, lane, frow);
+    case 16: return blk_tree_pentomino<16>(sm, ne, lane, frow);
+    case 17: return blk_tree_pentomino<17>(sm, ne, lane, frow);
+    case 18: return blk_tree_pentomino<18>(sm, ne, lane, frow);
+    case 19: return blk_tree_pentomino<19>(sm, ne, lane, frow);
+    default: return blk_tree_pentomino<20>(sm, ne, lane, frow);
+    }
+}
+
+// any-move test: OR_k (ANC & shift(FIT_s, cell_k)) over the shapes selected by COND
+#define BLK_ANY_CELL(slot, c) (sm.F[(slot) * BLK_FROWS + 4 + lane - ((c) >> 3)] >> (4 - ((c) & 7)))
+#define BLK_ANY_STEP(s, local, n, c0, c1, c2, c3, c4, nevar)                                                  \
+    if (nevar >> ((s) < BLK_NSHAPE_LE4 ? (s) : (local)) & 1u) {                                               \
+        if (lane < 20) {                                                                                      \
+            uint32_t d_ = BLK_ANY_CELL(BLK_SLOT(s, local), c0);                                               \
+            if ((n) > 1) d_ |= BLK_ANY_CELL(BLK_SLOT(s, local), c1);                                          \
+            if ((n) > 2) d_ |= BLK_ANY_CELL(BLK_SLOT(s, local), c2);                                          \
+            if ((n) > 3) d_ |= BLK_ANY_CELL(BLK_SLOT(s, local), c3);                                          \
+            if ((n) > 4) d_ |= BLK_ANY_CELL(BLK_SLOT(s, local), c4);                                          \
+            acc |= d_ & anc;                                                                                  \
+        }                                                                                                     \
+    }
+
+// held pieces with LEVEL (1..4) cells
+template <int LEVEL>
+__device__ __forceinline__ bool blk_any_level(BlkSmem &sm, uint32_t ne, uint32_t inv, uint32_t anc, int lane) {
+    uint32_t acc = 0u;
+#define BLK_Y(s, piece, local, n, c0, c1, c2, c3, c4) \
+    if ((n) == LEVEL && (inv >> (piece) & 1u)) BLK_ANY_STEP(s, local, n, c0, c1, c2, c3, c4, ne)
+    BLK_SHAPE_LIST(BLK_Y)
+#undef BLK_Y
+    return __any_sync(0xffffffffu, acc != 0u);
+}
+
+template <int PIECE>
+__device__ __forceinline__ bool blk_any_pentomino(BlkSmem &sm, uint32_t ne, uint32_t anc, int lane, int frow) {
+    const uint32_t ne5 = blk_tree_pentomino<PIECE>(sm, ne, lane, frow);
+    uint32_t acc = 0u;
+#define BLK_Y(s, piece, local, n, c0, c1, c2, c3, c4) \
+    if ((n) == 5 && (piece) == PIECE) BLK_ANY_STEP(s, local, n, c0, c1, c2, c3, c4, ne5)
+    BLK_SHAPE_LIST(BLK_Y)
+#undef BLK_Y
+    return __any_sync(0xffffffffu, acc != 0u);
+}
+
+// AI.check_moves (ai.py:36-42): does player c holding `inv` have any move on the board in sm.st?
+__device__ __forceinline__ int blk_any_move(BlkSmem &sm, int c, int round, uint32_t inv, int lane) {
+    if (inv == 0u || blk_allowed_and_anchors(sm, c, round, lane) == 0) return 0;
+    const uint32_t anc = lane < 20 ? sm.anc[lane] : 0u;
+    const int frow = lane < 20 ? lane + 4 : lane - 20;
+    uint32_t ne = blk_tree_root(sm, lane, frow);
+    __syncwarp();
+    if (blk_any_level<1>(sm, ne, inv, anc, lane)) return 1;
+    blk_tree_level<2>(sm, ne, inv, lane, frow);
+    if (blk_any_level<2>(sm, ne, inv, anc, lane)) return 1;
+    blk_tree_level<3>(sm, ne, inv, lane, frow);
+    if (blk_any_level<3>(sm, ne, inv, anc, lane)) return 1;
+    blk_tree_level<4>(sm, ne, inv, lane, frow);
+    if (blk_any_level<4>(sm, ne, inv, anc, lane)) return 1;
+#define BLK_P5(P)                                                                            \
+    if (inv >> (P) & 1u) {                                                                   \
+        __syncwarp();                                                                        \
+        if (blk_any_pentomino<P>(sm, ne, anc, lane, frow)) return 1;                         \
+    }
+    BLK_P5(9) BLK_P5(10) BLK_P5(11) BLK_P5(12) BLK_P5(13) BLK_P5(14)
+    BLK_P5(15) BLK_P5(16) BLK_P5(17) BLK_P5(18) BLK_P5(19) BLK_P5(20)
+#undef BLK_P5
+    return 0;
+}
+
+// Enumerate the legal moves of player c holding `inv` on the board in sm.st: action ids in the reference's order
+// into out[0..cap), returns the full count.
 __device__ __forceinline__ int blk_enumerate(BlkSmem &sm, int c, int round, uint32_t inv, int lane,
                                              int32_t *__restrict__ out, int cap) {
     const int na = blk_allowed_and_anchors(sm, c, round, lane);
-    if (na == 0) return 0;
+    if (na == 0 || inv == 0u) return 0;
+    const int frow = lane < 20 ? lane + 4 : lane - 20;
+    uint32_t ne = blk_tree_root(sm, lane, frow);
+    __syncwarp();
+    blk_tree_level<2>(sm, ne, inv, lane, frow);
+    blk_tree_level<3>(sm, ne, inv, lane, frow);
+    blk_tree_level<4>(sm, ne, inv, lane, frow);
     int base = 0;
     const uint32_t lt = (1u << lane) - 1u;
     for (int p = 0; p < BLK_NPIECE; p++) {
         if (!(inv >> p & 1u)) continue;
-        blk_fit_boards(sm, p, lane);
-        const int s0 = BLK_PIECE_SHAPE0[p], id0 = BLK_PIECE_ID0[p], nid = BLK_PIECE_ID0[p + 1] - id0;
-        const uint32_t e0 = lane < nid ? BLK_ID_TAB[id0 + lane] : 0u;
-        const uint32_t e1 = lane + 32 < nid ? BLK_ID_TAB[id0 + 32 + lane] : 0u;
-        const int f0 = ((int)(e0 & 127u) - s0) * 20, dx0 = (e0 >> 7) & 7, dy0 = (e0 >> 10) & 7;
-        const int f1 = ((int)(e1 & 127u) - s0) * 20, dx1 = (e1 >> 7) & 7, dy1 = (e1 >> 10) & 7;
-        const bool v0 = lane < nid, v1 = lane + 32 < nid;
+        const int id0 = BLK_PIECE_ID0[p], nid = BLK_PIECE_ID0[p + 1] - id0, sh0 = BLK_PIECE_SHAPE0[p];
+        const bool pent = nid > 32;                                      // 40 ids: the 12 pentominoes
+        uint32_t nep = ne;                                               // non-empty flags of shape s: bit s - foff
+        int soff = 0, foff = 0;
+        if (pent) {
+            nep = blk_tree_pentomino_dyn(sm, p, ne, lane, frow);
+            if (nep == 0u) continue;                                     // none of the piece's shapes fits anywhere
+            soff = BLK_NSHAPE_LE4 - sh0;                                 // shape s of this piece lives in slot s + soff
+            foff = sh0;
+        }
+        // lane = (orientation, shift) id of the piece: its shape's FIT board, the cell that sits on the anchor.
+        // A pentomino's ids 32..39 are tested for FOUR anchors per pass: lane = (anchor j = lane >> 3, id 32 + (lane & 7)).
+        const uint32_t e0 = lane < nid ? BLK_ID_TAB_G[id0 + lane] : 0u;
+        const uint32_t e1 = pent ? BLK_ID_TAB_G[id0 + 32 + (lane & 7)] : 0u;
+        const int s0 = lane < nid ? (int)(e0 & 127u) : foff, s1 = pent ? (int)(e1 & 127u) : foff;
+        const int sl0 = s0 + soff, sl1 = s1 + soff;
+        const bool v0 = lane < nid && (nep >> (s0 - foff) & 1u), v1 = pent && (nep >> (s1 - foff) & 1u);
+        if (__ballot_sync(0xffffffffu, v0 || v1) == 0u) continue;
+        const uint32_t *f0 = sm.F + sl0 * BLK_FROWS + 4 - (int)((e0 >> 10) & 7u);
+        const uint32_t *f1 = sm.F + sl1 * BLK_FROWS + 4 - (int)((e1 >> 10) & 7u);
+        const int xs0 = (int)((e0 >> 7) & 7u), xs1 = (int)((e1 >> 7) & 7u);
+        const int ok0 = (int)(e0 >> 13), ok1 = (int)(e1 >> 13);
+        // ids 32..39 of a pentomino ("pass B") are tested for the next four anchors at once every fourth iteration
+        const int j1 = lane >> 3;
+        const uint32_t lt8 = (1u << (lane & 7)) - 1u;
+        uint32_t mB = 0u;
+        bool hit1 = false;
         for (int ai = 0; ai < na; ai++) {
-            const int a = sm.alist[ai], ay = a / 20, ax = a - ay * 20;
-            int qx = ax - dx0, qy = ay - dy0;
-            bool ok0 = v0 && qx >= 0 && qy >= 0 && ((sm.F[f0 + max(qy, 0)] >> max(qx, 0)) & 1u);
-            uint32_t m0 = __ballot_sync(0xffffffffu, ok0), m1 = 0;
-            bool ok1 = false;
-            if (nid > 32) {
-                qx = ax - dx1; qy = ay - dy1;
-                ok1 = v1 && qx >= 0 && qy >= 0 && ((sm.F[f1 + max(qy, 0)] >> max(qx, 0)) & 1u);
-                m1 = __ballot_sync(0xffffffffu, ok1);
+            const int sub = ai & 3;
+            if (pent && sub == 0) {
+                const int a1 = sm.alist[ai + j1];                        // (the list is padded with never-fitting anchors)
+                hit1 = v1 && ((f1[a1 >> 8] >> ((a1 & 255) - xs1)) & 1u);
+                mB = __ballot_sync(0xffffffffu, hit1);
             }
-            if (EMIT) {
-                const int code = (p * 400 + a) * 40;
-                int pos = base + __popc(m0 & lt);
-                if (ok0 && pos < cap) out[pos] = code + (int)(e0 >> 13);
-                base += __popc(m0);
-                pos = base + __popc(m1 & lt);
-                if (ok1 && pos < cap) out[pos] = code + (int)(e1 >> 13);
-                base += __popc(m1);
-            } else if (m0 | m1) {
-                return 1;
-            }
+            const int a = sm.alist[ai], ay = a >> 8, ax4 = a & 255;
+            const bool hit = v0 && ((f0[ay] >> (ax4 - xs0)) & 1u);
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            const uint32_t mh = (mB >> (8 * sub)) & 255u;
+            if ((m | mh) == 0u) continue;
+            const int code = (p * 400 + ay * 20 + ax4 - 4) * 40;
+            int pos = base + __popc(m & lt);
+            if (hit && pos < cap) out[pos] = code + ok0;                 // anchor ai: ids 0..31 ...
+            base += __popc(m);
+            pos = base + __popc(mh & lt8);
+            if (hit1 && j1 == sub && pos < cap) out[pos] = code + ok1;   // ... then ids 32..39
+            base += __popc(mh);
         }
     }
     return base;
@@ -183,7 +321,7 @@ blokus_legal_kernel(const uint4 *__restrict__ st, int32_t *__restrict__ counts, 
         if ((flags & CRL_FLAG_AUTO_RESET) && (sm.st[85] >> 16 & 1u)) blk_new_state(sm, lane);
         const uint32_t meta = sm.st[85];
         const int c = player >= 0 ? player : (int)(meta >> 8 & 3u);
-        const int n = blk_enumerate<true>(sm, c, (int)(meta & 0xffu), sm.st[80 + c], lane, ids + g * cap, cap);
+        const int n = blk_enumerate(sm, c, (int)(meta & 0xffu), sm.st[80 + c], lane, ids + g * cap, cap);
         if (lane == 0) {
             counts[g] = n;
             if (stats) atomicAdd(&sm_stat[ST_NVALID], n);
@@ -266,7 +404,7 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
             uint32_t iq = 0;
 #pragma unroll
             for (int r = 0; r < 4; r++) iq |= (r == q) ? inv[r] : 0u;
-            any = blk_enumerate<false>(sm, q, round, iq, lane, nullptr, 0);
+            any = blk_any_move(sm, q, round, iq, lane);
         }
         const int terminal = !any;
         int reward = 0, winners = 0;

@@ -73,10 +73,55 @@ def build():
     return shapes, piece_shape0, piece_id0, ids
 
 
+def connected(cells):
+    cells = set(cells)
+    seen, todo = set(), [next(iter(cells))]
+    while todo:
+        c = todo.pop()
+        if c in seen:
+            continue
+        seen.add(c)
+        for d in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            n = (c[0] + d[0], c[1] + d[1])
+            if n in cells and n not in seen:
+                todo.append(n)
+    return len(seen) == len(cells)
+
+
+def build_tree(shapes):
+    """The 91 shapes are exactly the fixed polyominoes of 1..5 cells, so every shape s of n >= 2 cells is a shape
+    of n - 1 cells ("parent") plus one cell c:   FIT_s[q] = FIT_parent[q + off] & A[q + c]   with off = the parent's
+    bounding-box corner inside s.  All 91 FIT boards then cost 90 AND steps instead of 414 - 91.
+    need[s] = pieces whose own shapes are s or descend from s (a shape is only built if one of them is held)."""
+    index = {cells: i for i, (_, cells) in enumerate(shapes)}
+    tree = [None] * len(shapes)
+    for i, (_, cells) in enumerate(shapes):
+        if len(cells) == 1:
+            continue
+        best = None
+        for c in cells:
+            rest = [x for x in cells if x != c]
+            if not connected(rest):
+                continue
+            mx, my = min(x for x, _ in rest), min(y for _, y in rest)
+            par = index[tuple(sorted((x - mx, y - my) for x, y in rest))]
+            cand = (par, mx, my, c[0], c[1])
+            if best is None or cand < best:
+                best = cand
+        assert best is not None and best[0] < i
+        tree[i] = best
+    need = [1 << p for p, _ in shapes]
+    for i in range(len(shapes) - 1, 0, -1):
+        need[tree[i][0]] |= need[i]
+    return tree, need
+
+
 def emit(path):
     shapes, piece_shape0, piece_id0, ids = build()
     assert len(shapes) == 91 and len(ids) == 712
     assert sum(len(s[1]) for s in shapes) == 414
+    assert [len(c) for _, c in shapes] == sorted(len(c) for _, c in shapes)       # shapes are ordered by size
+    tree, need = build_tree(shapes)
     L = []
     L.append("// GENERATED by gen_blokus_tables.py -- do not edit.  See that file for the derivation.")
     L.append("#pragma once")
@@ -108,6 +153,31 @@ def emit(path):
     for i in range(0, len(row), 8):
         L.append("    " + ", ".join(row[i:i + 8]) + ",")
     L.append("};")
+    L.append("// the same table in global memory for lane-indexed reads (a divergent __constant__ read is serialised)")
+    L.append("__device__ const uint32_t BLK_ID_TAB_G[BLK_NID] = {")
+    for i in range(0, len(row), 8):
+        L.append("    " + ", ".join(row[i:i + 8]) + ",")
+    L.append("};")
+    L.append("// Polyomino tree (see build_tree in the generator): X(level, s, piece, local, parent, px, py, cx, cy, need) for")
+    L.append("// s = 1..90 in shape order (= by size); FIT_s[q] = FIT_parent[q + (px, py)] & A[q + (cx, cy)]; local = s - first")
+    L.append("// shape of its piece; `need` = pieces that need s (own piece + descendants).  Expanded into straight-line code,")
+    L.append("// so every field is an immediate.  Shapes of 5 cells are leaves: need == 1 << piece.")
+    L.append("#define BLK_NSHAPE_LE4 %d" % sum(1 for _, c in shapes if len(c) <= 4))
+    L.append("#define BLK_TREE_LIST(X) \\")
+    for i in range(1, len(shapes)):
+        par, px, py, cx, cy = tree[i]
+        pc = shapes[i][0]
+        if len(shapes[i][1]) == 5:
+            assert need[i] == 1 << pc and len(shapes[par][1]) == 4
+        L.append("    X(%d, %d, %d, %d, %d, %d, %d, %d, %d, 0x%06xu) \\" % (len(shapes[i][1]), i, pc, i - piece_shape0[pc], par, px, py,
+                                                                       cx, cy, need[i]))
+    L.append("")
+    L.append("// Shapes with their cells: Y(s, piece, local, ncells, c0..c4) with c = dx | dy << 3 (unused cells repeat cell 0)")
+    L.append("#define BLK_SHAPE_LIST(Y) \\")
+    for i, (pc, cells) in enumerate(shapes):
+        cl = list(cells) + [cells[0]] * (5 - len(cells))
+        L.append("    Y(%d, %d, %d, %d, %s) \\" % (i, pc, i - piece_shape0[pc], len(cells), ", ".join(str(dx | dy << 3) for dx, dy in cl)))
+    L.append("")
     open(path, "w").write("\n".join(L) + "\n")
 
 
