@@ -29,6 +29,7 @@ SIGNATURES = {
     "crl_tron_policy_random": (_int, [_vp, _u64, _u64, _u32, _i64, _vp]),
     "crl_tron_rollout": (_int, [_vp, _vp, _vp, _u64, _u64, _u32, _int, _i64, _int, _int, _vp]),
     "crl_tron_observe": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
+    "crl_tron_ranking": (_int, [_vp, _vp, _i64, _int, _int, _vp]),
     "crl_tron_pack": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
     "crl_ttt_cells": (_int, [_int]),
     "crl_ttt_lines": (_int, [_int, C.POINTER(_u32), _int]),

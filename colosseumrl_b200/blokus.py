@@ -29,6 +29,36 @@ def string_to_action(action_str: str) -> int:
     return ((PIECE_NAMES.index(piece) * 400 + y * 20 + x) * 8 + ORIENTATIONS.index(orientation[:-1])) * 5 + int(orientation[-1])
 
 
+def _rotate_action_ids(ids, player, inverse: bool):
+    """Action ids between the board frame and a player's rotated observation frame (np.rot90(k=-player),
+    BlokusEnvironment.py:31-32): index -> M[player] @ (index - 9.5) + 9.5, orientation +- 2 * player, shift unchanged
+    (:553-628; matrices board.py:52-73).  Works on ints and on integer tensors / arrays; -1 (pass) stays -1."""
+    k, o, cell, piece = ids % 5, (ids // 5) % 8, (ids // 40) % 400, ids // 16000
+    x, y = cell % 20, cell // 20
+    r = (-player if inverse else player) % 4
+    if r == 1:
+        x, y = 19 - y, x
+    elif r == 2:
+        x, y = 19 - x, 19 - y
+    elif r == 3:
+        x, y = y, 19 - x
+    o = (o + (-2 * player if inverse else 2 * player)) % 8
+    out = ((piece * 400 + y * 20 + x) * 8 + o) * 5 + k
+    if isinstance(ids, int):
+        return out if ids >= 0 else -1
+    return out * (ids >= 0) - (ids < 0) * 1
+
+
+def real_action_to_player_perspective(ids, player: int):
+    """convert_real_action_to_player_perspective_action (BlokusEnvironment.py:553-588) on action ids."""
+    return _rotate_action_ids(ids, int(player), False)
+
+
+def player_perspective_action_to_real(ids, player: int):
+    """convert_player_perspective_action_to_real_action (:591-628) on action ids."""
+    return _rotate_action_ids(ids, int(player), True)
+
+
 @dataclass
 class BlokusBatchState:
     packed: torch.Tensor                        # int32 [B, 22, 4]: 352 bytes per game
@@ -93,6 +123,12 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         slot = torch.arange(ids.shape[1], device=self.device)[None]
         return (((ids == action[:, None]) & (slot < counts[:, None])).any(dim=1) & (action >= 0)).to(torch.uint8)
 
+    def player_perspective_valid_actions(self, state: BlokusBatchState, player: int):
+        """player_perspective_valid_actions (:502-551): the valid list of `player`, same order, every id rotated into
+        that player's observation frame.  (counts, ids) like valid_actions."""
+        counts, ids = self.valid_actions(state, player, count_stats=False)
+        return counts, real_action_to_player_perspective(ids, player)
+
     def next_state(self, state: BlokusBatchState, players, actions, out: Optional[BlokusBatchState] = None):
         """next_state (:357-451).  actions: int32 [B] action ids (-1 = pass).
         Returns (new_state, new_players mask, reward int8 [B] (mover's), terminal uint8 [B], winners mask uint8 [B])."""
@@ -120,6 +156,7 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         return torch.stack([(s >> (8 * p)) & 0xff for p in range(4)], dim=1)
 
     def state_to_observation(self, state: BlokusBatchState, player: int) -> Dict[str, torch.Tensor]:
+        """state_to_observation (:721-768).  player = -1: absolute unpack; -2: every game from its mover's perspective."""
         B = self.batch
         board = torch.empty((B, 20, 20), dtype=torch.int8, device=self.device)
         pieces = torch.empty((B, 4, 21), dtype=torch.uint8, device=self.device)
@@ -128,8 +165,9 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         self._check(self._lib.crl_blokus_observe(state.packed.data_ptr(), int(player), board.data_ptr(), pieces.data_ptr(),
                                                  score.data_ptr(), meta.data_ptr(), B, self._stream))
         obs = {"board": board, "pieces": pieces, "score": score,
-               "player": torch.full((B, 1), int(player), dtype=torch.int32, device=self.device)}
-        if player < 0:
+               "player": meta[:, 1:2].clone() if player == -2 else
+               torch.full((B, 1), int(player), dtype=torch.int32, device=self.device)}
+        if player == -1:
             obs.update(round=meta[:, 0], mover=meta[:, 1], terminal=meta[:, 2], episode_steps=meta[:, 3])
         return obs
 

@@ -490,6 +490,7 @@ __global__ void blokus_observe_kernel(const uint4 *__restrict__ st4, long long B
     long long g = idx / 400;
     int cell = (int)(idx - g * 400), i = cell / 20, j = cell - i * 20;
     const uint32_t *s = st + g * BLK_WORDS;
+    if (player == -2) player = (int)(s[85] >> 8 & 3u);      // CRL_PLAYER_MOVER: the game's current mover
     int si = i, sj = j;                                     // source cell of np.rot90(k=-player)
     if (player == 1) { si = 19 - j; sj = i; }
     else if (player == 2) { si = 19 - i; sj = 19 - j; }

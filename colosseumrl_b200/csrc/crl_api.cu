@@ -288,6 +288,17 @@ int crl_tron_observe(const void *state, int player, int8_t *board, int32_t *head
     return check_launch("tron_observe_kernel");
 }
 
+int crl_tron_ranking(const void *state, uint8_t *ranking, int64_t B, int N, int P, crl_stream_t stream) {
+    int rc = tron_check(N, P, B);
+    if (rc) return rc;
+    if (!state || !ranking) return fail(CRL_ERR_ARG, "crl_tron_ranking: null pointer%s");
+    TronParams prm;
+    if ((rc = tron_params(N, P, prm))) return rc;
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(tron_ranking_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state, (long long)B, prm, ranking);
+    return check_launch("tron_ranking_kernel");
+}
+
 int crl_tron_pack(void *state, const int8_t *board, const int32_t *heads, const int32_t *directions,
                   const int32_t *deaths, int64_t B, int N, int P, crl_stream_t stream) {
     int rc = tron_check(N, P, B);

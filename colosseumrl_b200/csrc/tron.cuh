@@ -526,6 +526,20 @@ __global__ void tron_observe_kernel(const uint4 *__restrict__ st, long long B, T
     }
 }
 
+// compute_ranking (TronGridEnvironment.py:483-508) of an arbitrary state, without stepping it: ranking byte per
+// environment (2 bits per player), same code path as the ranking fused into the step
+__global__ void tron_ranking_kernel(const uint4 *__restrict__ st, long long B, TronParams prm, uint8_t *__restrict__ ranking) {
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B) return;
+    const uint4 h = st[12ll * B + e];
+    TronCtx c;
+    c.X = h.x; c.Y = h.y; c.Z = h.z; c.W = h.w;
+    c.D4 = (h.y >> 5) & 0x07070707u;
+    TronOut o;
+    tron_phase3(c, prm, o);
+    ranking[e] = (uint8_t)o.rank8;
+}
+
 // import a reference-layout state (board int8[B][N][N], heads (y*N+x) / directions / deaths int32[B][P]);
 // one thread per environment (import path, not performance critical)
 __global__ void tron_pack_kernel(uint4 *__restrict__ st, long long B, TronParams prm,

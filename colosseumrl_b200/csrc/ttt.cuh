@@ -276,6 +276,7 @@ __global__ void ttt_observe_kernel(const uint4 *__restrict__ st, long long B, TT
     int c = (int)(idx - e * prm.cells);
     TTTEnv s;
     ttt_decode(s, st[e]);
+    if (player == -2) player = s.mover;                     // CRL_PLAYER_MOVER: the game's current mover
     int v = -1;
 #pragma unroll
     for (int p = 0; p < 4; p++) v = (s.m[p] >> c & 1) ? p : v;

@@ -121,9 +121,13 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
 
     def compute_ranking(self, state: TronBatchState, players=None, winners=None) -> torch.Tensor:
         """TronGridEnvironment.compute_ranking (:483-508), fused into the step: uint8 [B, P]."""
-        if state.result is None:
-            raise ValueError("ranking is produced by next_state; this state has not been stepped yet")
-        rk = state.result[:, 7].to(torch.int32)
+        if state.result is not None:
+            rk = state.result[:, 7].to(torch.int32)
+        else:                                   # a state that was not produced by a step (imported / fresh)
+            rk8 = torch.empty((self.batch,), dtype=torch.uint8, device=self.device)
+            self._check(self._lib.crl_tron_ranking(state.packed.data_ptr(), rk8.data_ptr(), self.batch, self.N,
+                                                   self.num_players, self._stream))
+            rk = rk8.to(torch.int32)
         shifts = 2 * torch.arange(self.num_players, device=self.device)
         return ((rk[:, None] >> shifts[None]) & 3).to(torch.uint8)
 

@@ -1,0 +1,54 @@
+"""Vectorised reset / step wrapper: the batched analogue of the reference's RLlib adapter
+(colosseumrl/envs/wrappers/rllib.py:8-55, envs/tron/rllib.py:13-66), which drives ONE game per Python object through
+new_state -> state_to_observation and next_state -> state_to_observation -> reward / done dicts.  Here one object
+steps B games per call and the per-agent dicts become tensors:
+
+    venv = VectorEnv(BatchedTronGridEnvironment("", batch=4096, auto_reset=True))
+    obs = venv.reset()                       # {"board": [B, P, N, N], "heads": [B, P, P], ...}
+    obs, rewards, dones, info = venv.step(actions)     # rewards [B, P], dones uint8 [B]
+
+Simultaneous-move games (Tron) are observed from every seat; turn-based games (Blokus, Tic Tac Toe) from the seat of
+each game's next mover (`info["mover"]`).  Finished games restart on their next step when the environment was built
+with auto_reset=True (the step kernels do that themselves); `dones` marks the step that ended an episode.
+"""
+from typing import Dict
+
+import torch
+
+
+class VectorEnv:
+    def __init__(self, env):
+        self.env = env
+        self.state = None
+        self.simultaneous = hasattr(env, "remove_on_death")          # Tron: all live players act every step
+
+    @property
+    def num_envs(self) -> int:
+        return self.env.batch
+
+    @property
+    def num_players(self) -> int:
+        return self.env.max_players
+
+    def _observe(self) -> Dict[str, torch.Tensor]:
+        if self.simultaneous:
+            per_seat = [self.env.state_to_observation(self.state, p) for p in range(self.num_players)]
+            return {k: torch.stack([o[k] for o in per_seat], dim=1) for k in per_seat[0]}
+        return self.env.state_to_observation(self.state, -2)          # CRL_PLAYER_MOVER
+
+    def reset(self) -> Dict[str, torch.Tensor]:
+        self.state, _ = self.env.new_state()
+        return self._observe()
+
+    def valid_actions(self):
+        """Valid actions of every game's acting player(s), in the batched environment's own format."""
+        return self.env.valid_actions(self.state, -1)
+
+    def step(self, actions):
+        """actions: the batched environment's action tensor (Tron int8 [B, 4]; Blokus int32 [B] ids; TTT int8 [B])."""
+        new, players, rewards, terminal, winners = self.env.next_state(self.state, None, actions, out=self.state)
+        self.state = new
+        info = {"players": players, "winners": winners}
+        if not self.simultaneous:                                     # players = 1 << next mover
+            info["mover"] = (players >> 1) - (players >> 3)           # 1, 2, 4, 8 -> 0, 1, 2, 3
+        return self._observe(), rewards, terminal, info

@@ -29,6 +29,9 @@ extern "C" {
 #define CRL_ERR_CUDA 2
 #define CRL_ERR_UNSUPPORTED 3
 
+#define CRL_PLAYER_ABSOLUTE (-1) /* observe: plain unpack, no perspective transform */
+#define CRL_PLAYER_MOVER (-2)    /* observe (Blokus, Tic Tac Toe): each game from the perspective of its current mover */
+
 #define CRL_FLAG_AUTO_RESET 1 /* an environment whose stored terminal flag is set is replaced by new_state() before the step */
 
 /* statistics buffer: int64[CRL_STAT_ROWS][CRL_NSTAT] on the device, accumulated (+=) by step / rollout kernels.
@@ -86,6 +89,9 @@ int crl_tron_rollout(void *state, uint8_t *result_or_null, int64_t *stats_or_nul
  * board int8[B][N][N]; heads (y*N+x) / directions / deaths int32[B][P] (may be NULL); terminal u8[B] (may be NULL) */
 int crl_tron_observe(const void *state, int player, int8_t *board, int32_t *heads, int32_t *directions,
                      int32_t *deaths, uint8_t *terminal_or_null, int64_t B, int N, int P, crl_stream_t stream);
+/* compute_ranking (TronGridEnvironment.py:483-508) of any state, without stepping it: ranking u8[B], 2 bits per
+ * player (the same value crl_tron_step writes into result byte 7) */
+int crl_tron_ranking(const void *state, uint8_t *ranking, int64_t B, int N, int P, crl_stream_t stream);
 /* import a reference-layout state */
 int crl_tron_pack(void *state, const int8_t *board, const int32_t *heads, const int32_t *directions,
                   const int32_t *deaths, int64_t B, int N, int P, crl_stream_t stream);

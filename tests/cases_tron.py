@@ -127,6 +127,14 @@ def case_adversarial(be):
             exp = g["o_ranking"][m][:, :P]
             ok = exp >= 0   # players owning no cell are absent from the reference's Counter (hand-built states only)
             assert (res["ranking"][:, :P][ok] == exp[ok]).all()
+            # compute_ranking of the INPUT states through the standalone entry point
+            rk = be.zeros((int(m.sum()),), np.uint8)
+            be.check(be.lib.crl_tron_ranking(be.ptr(st), be.ptr(rk), int(m.sum()), N, P, be.stream))
+            rk = be.download(rk).astype(np.int64)
+            got = np.stack([(rk >> (2 * p)) & 3 for p in range(4)], axis=1)[:, :P]
+            exp = g["i_ranking"][m][:, :P]
+            ok = exp >= 0
+            assert (got[ok] == exp[ok]).all()
 
 
 def case_rollout_vs_oracle(be, N=19, P=4, B=200, K=48, seed=5, env0=1000):
