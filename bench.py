@@ -192,7 +192,7 @@ def _pipelined_e2e_step(work, k, probe_col):
     work.inflight.append(sp)
     r = 0
     if len(work.inflight) >= E2E_DEPTH:
-        r = int(work.inflight.pop(0).wait()[0, probe_col])       # the host reads the result record
+        r = int(work.inflight.pop(0).wait()[0, probe_col])       # the host reads the result record (numpy view, pinned)
     return r
 
 

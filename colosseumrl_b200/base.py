@@ -34,7 +34,7 @@ class HostStepper:
 
         stepper = env.host_stepper(state)
         stepper.actions[...] = my_policy(...)      # write into the pinned action buffer
-        result = stepper()                         # replay + wait; `result` is the pinned uint8 record tensor
+        result = stepper()                         # replay + wait; `result` is a numpy view of the pinned uint8 records
     An actor that serves two (or more) environment batches can pipeline them: `a.launch(); b.wait(); ...`; give each
     stepper its own `stream` and the copy engines of one batch overlap the step kernel of another.
 
@@ -48,6 +48,8 @@ class HostStepper:
         self._dev_actions = torch.zeros(action_shape, dtype=action_dtype, device=env.device)
         env.step_(state, self._dev_actions, out=state)          # allocates state.result; warms the launch path
         self.result = torch.empty(state.result.shape, dtype=torch.uint8).pin_memory()
+        self.result_np = self.result.numpy()                    # zero-copy numpy view of the pinned record (cheap reads)
+        self.actions_np = self.actions.numpy()
         torch.cuda.synchronize(env.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -76,7 +78,7 @@ class HostStepper:
         rc = self._rt.cudaEventSynchronize(self._done)
         if rc:
             raise RuntimeError("HostStepper wait failed: cudaError %d" % rc)
-        return self.result
+        return self.result_np
 
     def __del__(self):
         try:

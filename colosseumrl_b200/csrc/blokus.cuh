@@ -477,41 +477,53 @@ __global__ void blokus_reset_kernel(uint4 *__restrict__ st, const uint8_t *__res
     st[idx] = (v == 20) ? make_uint4(full, full, full, full) : make_uint4(0, 0, 0, 0);
 }
 
-// state_to_observation (BlokusEnvironment.py:721-768), one thread per output cell.
+// state_to_observation (BlokusEnvironment.py:721-768): one warp per game.  The 352-byte state is loaded with 22
+// coalesced 128-bit accesses into shared memory; lane l then produces output cells l, l + 32, ... so that every
+// store instruction of the warp writes 32 consecutive bytes.
 //  player >= 0: board int8[B][20][20] of relative player ids (-1 empty) rotated by np.rot90(k=-player);
 //               pieces u8[B][4][21] rows by relative id; score int32[B][4] rolled by -player.
-//  player <  0: absolute unpack: board = Board.board_contents (0 empty, 1..4 colour), pieces / score in seat order.
+//  player == -1: absolute unpack: board = Board.board_contents (0 empty, 1..4 colour), pieces / score in seat order.
+//  player == -2: like player >= 0 with every game seen by its own current mover (CRL_PLAYER_MOVER).
 //  meta (optional) int32[B][4] = round, mover, terminal, episode steps.
-__global__ void blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, int8_t *__restrict__ board,
-                                      uint8_t *__restrict__ pieces, int32_t *__restrict__ score, int32_t *__restrict__ meta) {
-    const uint32_t *st = (const uint32_t *)st4;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * 400) return;
-    long long g = idx / 400;
-    int cell = (int)(idx - g * 400), i = cell / 20, j = cell - i * 20;
-    const uint32_t *s = st + g * BLK_WORDS;
-    if (player == -2) player = (int)(s[85] >> 8 & 3u);      // CRL_PLAYER_MOVER: the game's current mover
-    int si = i, sj = j;                                     // source cell of np.rot90(k=-player)
-    if (player == 1) { si = 19 - j; sj = i; }
-    else if (player == 2) { si = 19 - i; sj = 19 - j; }
-    else if (player == 3) { si = j; sj = 19 - i; }
-    int v = -1;
-    for (int c = 0; c < 4; c++) v = (s[20 * c + si] >> sj & 1u) ? c : v;
-    if (player >= 0) v = v < 0 ? -1 : ((v - player) & 3);   // _relative_player_id (:46-50)
-    else v = v + 1;
-    board[idx] = (int8_t)v;
-    if (cell < 84) {                                        // pieces[rel][piece]
-        int r = cell / 21, p = cell - r * 21;
-        int src = player >= 0 ? ((r + player) & 3) : r;
-        pieces[g * 84 + cell] = (uint8_t)(s[80 + src] >> p & 1u);
+__global__ void __launch_bounds__(32 * BLK_WARPS)
+blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, int8_t *__restrict__ board,
+                      uint8_t *__restrict__ pieces, int32_t *__restrict__ score, int32_t *__restrict__ meta) {
+    __shared__ uint32_t sst[BLK_WARPS][BLK_WORDS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
+    if (g >= B) return;
+    uint32_t *s = sst[wid];
+    if (lane < BLK_VEC) {
+        const uint4 v = ld_stream(st4 + g * BLK_VEC + lane);
+        s[4 * lane + 0] = v.x; s[4 * lane + 1] = v.y; s[4 * lane + 2] = v.z; s[4 * lane + 3] = v.w;
     }
-    if (cell < 4) {
-        int src = player >= 0 ? ((cell + player) & 3) : cell;
-        score[g * 4 + cell] = (int)(s[84] >> (8 * src) & 0xffu);
+    __syncwarp();
+    if (player == -2) player = (int)(s[85] >> 8 & 3u);
+    for (int idx = lane; idx < 400; idx += 32) {
+        const int i = idx / 20, j = idx - i * 20;
+        int si = i, sj = j;                                 // source cell of np.rot90(k=-player)
+        if (player == 1) { si = 19 - j; sj = i; }
+        else if (player == 2) { si = 19 - i; sj = 19 - j; }
+        else if (player == 3) { si = j; sj = 19 - i; }
+        int v = -1;
+#pragma unroll
+        for (int c = 0; c < 4; c++) v = (s[20 * c + si] >> sj & 1u) ? c : v;
+        if (player >= 0) v = v < 0 ? -1 : ((v - player) & 3);   // _relative_player_id (:46-50)
+        else v = v + 1;
+        board[g * 400 + idx] = (int8_t)v;
+    }
+    for (int idx = lane; idx < 84; idx += 32) {             // pieces[rel][piece]
+        const int r = idx / 21, p = idx - r * 21;
+        const int src = player >= 0 ? ((r + player) & 3) : r;
+        pieces[g * 84 + idx] = (uint8_t)(s[80 + src] >> p & 1u);
+    }
+    if (lane < 4) {
+        const int src = player >= 0 ? ((lane + player) & 3) : lane;
+        score[g * 4 + lane] = (int)(s[84] >> (8 * src) & 0xffu);
         if (meta) {
-            uint32_t m = s[85];
-            meta[g * 4 + cell] = cell == 0 ? (int)(m & 0xffu) : cell == 1 ? (int)(m >> 8 & 3u)
-                                 : cell == 2 ? (int)(m >> 16 & 1u) : (int)s[86];
+            const uint32_t m = s[85];
+            meta[g * 4 + lane] = lane == 0 ? (int)(m & 0xffu) : lane == 1 ? (int)(m >> 8 & 3u)
+                                 : lane == 2 ? (int)(m >> 16 & 1u) : (int)s[86];
         }
     }
 }

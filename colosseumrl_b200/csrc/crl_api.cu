@@ -279,12 +279,17 @@ int crl_tron_observe(const void *state, int player, int8_t *board, int32_t *head
                      int32_t *deaths, uint8_t *terminal, int64_t B, int N, int P, crl_stream_t stream) {
     int rc = tron_check(N, P, B);
     if (rc) return rc;
-    if (!state || !board || player >= P) return fail(CRL_ERR_ARG, "crl_tron_observe: bad argument%s");
+    if (!state || !board || player >= P || player < -3 || player == -2) return fail(CRL_ERR_ARG, "crl_tron_observe: bad argument%s");
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(tron_observe_kernel, blocks_for(B * N * N, 256), 256, (cudaStream_t)stream, (const uint4 *)state,
-               (long long)B, prm, player, board, heads, directions, deaths, terminal);
+    const int img_bytes = (TRON_OBS_TILE * (player == -3 ? P : 1) * N * N + 15) & ~15;
+    if (player == -3)
+        CRL_LAUNCH_SMEM(tron_observe_kernel<true>, blocks_for(B, TRON_OBS_TILE), 128, img_bytes, (cudaStream_t)stream,
+                        (const uint4 *)state, (long long)B, prm, player, board, heads, directions, deaths, terminal);
+    else
+        CRL_LAUNCH_SMEM(tron_observe_kernel<false>, blocks_for(B, TRON_OBS_TILE), 128, img_bytes, (cudaStream_t)stream,
+                        (const uint4 *)state, (long long)B, prm, player, board, heads, directions, deaths, terminal);
     return check_launch("tron_observe_kernel");
 }
 
@@ -434,9 +439,9 @@ int crl_ttt_observe(const void *state, int player, int8_t *board, int8_t *winner
     TTTParams prm;
     int rc = ttt_params(n, prm);
     if (rc) return rc;
-    if (!state || !board || B < 0 || player >= n) return fail(CRL_ERR_ARG, "crl_ttt_observe: bad argument%s");
+    if (!state || !board || B < 0 || player >= n || player < -2) return fail(CRL_ERR_ARG, "crl_ttt_observe: bad argument%s");
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(ttt_observe_kernel, blocks_for(B * prm.cells, 256), 256, (cudaStream_t)stream, (const uint4 *)state,
+    CRL_LAUNCH(ttt_observe_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state,
                (long long)B, prm, player, board, winner, mover);
     return check_launch("ttt_observe_kernel");
 }
@@ -494,10 +499,10 @@ int crl_blokus_policy_random(const int32_t *counts, const int32_t *action_ids, i
 
 int crl_blokus_observe(const void *state, int player, int8_t *board, uint8_t *pieces, int32_t *score, int32_t *meta,
                        int64_t B, crl_stream_t stream) {
-    if (!state || !board || !pieces || !score || B < 0 || player > 3) return fail(CRL_ERR_ARG, "crl_blokus_observe: bad argument%s");
+    if (!state || !board || !pieces || !score || B < 0 || player > 3 || player < -2) return fail(CRL_ERR_ARG, "crl_blokus_observe: bad argument%s");
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(blokus_observe_kernel, blocks_for(B * 400, 256), 256, (cudaStream_t)stream, (const uint4 *)state, (long long)B,
-               player, board, pieces, score, meta);
+    CRL_LAUNCH(blokus_observe_kernel, blocks_for(B, BLK_WARPS), 32 * BLK_WARPS, (cudaStream_t)stream, (const uint4 *)state,
+               (long long)B, player, board, pieces, score, meta);
     return check_launch("blokus_observe_kernel");
 }
 

@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 #include <cuda.h>            // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
 #define CRL_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define CRL_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// dynamic shared memory (sized at launch); the emulator gives it its maximum size statically
+#define CRL_DYN_SMEM(name, maxbytes) extern __shared__ __align__(128) uint8_t name[]
 // launch with the programmatic-stream-serialization attribute (PDL); the kernel must call pdl_wait() before it
 // touches memory written by its predecessor in the stream
 #define CRL_LAUNCH_PDL(kernel, grid_, block_, stream_, ...)                                         \
@@ -24,6 +27,9 @@
 #define CRL_LAUNCH(kernel, grid, block, stream, ...) \
     hostsim::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
 #define CRL_LAUNCH_PDL CRL_LAUNCH
+#define CRL_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+    hostsim::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
+#define CRL_DYN_SMEM(name, maxbytes) static __attribute__((aligned(128))) uint8_t name[maxbytes]
 #endif
 
 #define CRL_NSTAT 32

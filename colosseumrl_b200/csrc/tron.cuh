@@ -494,36 +494,126 @@ __global__ void tron_reset_kernel(uint4 *__restrict__ state, const uint8_t *__re
     state[idx] = val;
 }
 
-// state_to_observation (TronGridEnvironment.py:385-405): one thread per board cell.  player < 0 => absolute
-// view (plain unpack: board values p+1, vectors unrolled).  board int8[B][N][N]; heads/dirs/deaths int32[B][P]
-// with heads as y*N + x like the reference.
-__global__ void tron_observe_kernel(const uint4 *__restrict__ st, long long B, TronParams prm, int player,
-                                    int8_t *__restrict__ board, int32_t *__restrict__ heads,
-                                    int32_t *__restrict__ dirs, int32_t *__restrict__ deaths,
-                                    uint8_t *__restrict__ terminal) {
+// state_to_observation (TronGridEnvironment.py:385-405).  A CTA handles a tile of 16 environments: 13 bulk copies
+// bring their packed state into shared memory, its 4 warps unpack 4 environments each into a shared-memory image of
+// the dense output, and ONE bulk copy writes the tile's boards (16 * nview * N*N contiguous bytes, always 16-byte
+// aligned and a multiple of 16 bytes) back to HBM.
+// Unpacking is byte-SWAR: lane l owns cells 128 k + 4 l .. + 3 (k = 0..2): the 4 bits of every plane are spread to
+// 4 bytes with one multiply + mask, and the relabelled owner is sum_q plane_q * newid_q with newid_q a constant of
+// (plane q, viewer) -- the relabelling of CyTronGrid.pyx:65-71 costs nothing.
+//   player >= 0 : that player's view (board relabelled, vectors rolled py:392)
+//   player == -1: absolute view (plain unpack: board values p+1)
+//   player == -3: ALL P views at once (CRL_PLAYER_ALL, nview = P)
+// board int8[B][nview][N][N]; heads (y*N + x like the reference) / dirs / deaths int32[B][nview][P]; terminal u8[B].
+#define TRON_OBS_TILE 16
+#define TRON_OBS_MAXBYTES (TRON_OBS_TILE * 4 * 384)
+
+// board value LUT of one view (owner 0 empty / q + 1 -> value) as the two source words of a PRMT
+__device__ __forceinline__ void tron_view_lut(int viewer, int P, uint32_t &lo, uint32_t &hi) {
+    uint32_t id[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int x = q + 1;                                       // absolute: board value = player + 1
+        if (viewer >= 0) { x = q - viewer; x += x < 0 ? P : 0; x += 1; }
+        id[q] = (uint32_t)(q < P ? x : 0);
+    }
+    lo = id[0] << 8 | id[1] << 16 | id[2] << 24;
+    hi = id[3];
+}
+
+__device__ __forceinline__ void tron_obs_store4(uint8_t *o, uint32_t v, int c0, int NN, bool guard) {
+    if (!guard) {
+        o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); o[3] = (uint8_t)(v >> 24);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (c0 + j < NN) o[j] = (uint8_t)(v >> (8 * j));
+    }
+}
+
+template <bool ALL>
+__global__ void __launch_bounds__(128)
+tron_observe_kernel(const uint4 *__restrict__ st, long long B, TronParams prm, int player,
+                    int8_t *__restrict__ board, int32_t *__restrict__ heads, int32_t *__restrict__ dirs,
+                    int32_t *__restrict__ deaths, uint8_t *__restrict__ terminal) {
+    __shared__ __align__(128) TronTile<TRON_OBS_TILE> tile;
+    CRL_DYN_SMEM(img, TRON_OBS_MAXBYTES);                 // TRON_OBS_TILE * nview * N*N bytes (rounded up to 16)
+    __shared__ __align__(8) uint64_t bar[2];
+    constexpr int PL = TronTile<TRON_OBS_TILE>::PL;
     const int N = prm.N, P = prm.P, NN = N * N;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * NN) return;
-    long long e = idx / NN;
-    int c = (int)(idx - e * NN);
-    int w = c >> 6, b = c & 63;
-    int v = 0;
-    for (int p = 0; p < P; p++) {
-        uint4 q = st[(long long)(3 * p + (w >> 1)) * B + e];
-        uint64_t word = (w & 1) ? ((uint64_t)q.z | (uint64_t)q.w << 32) : ((uint64_t)q.x | (uint64_t)q.y << 32);
-        if ((word >> b) & 1) v = p + 1;
+    const long long e0 = (long long)blockIdx.x * TRON_OBS_TILE;
+    const int n = (int)min((long long)TRON_OBS_TILE, B - e0);
+#ifndef CRL_HOSTSIM
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_expect_tx(&bar[0], (uint32_t)(TRON_VEC * n * 16));
+        const uint4 *src = st + e0;
+        uint4 *dst = &tile.v[0][0];
+#pragma unroll 1
+        for (int v = 0; v < TRON_VEC; v++, src += B, dst += TRON_OBS_TILE) bulk_g2s(dst, src, (uint32_t)(n * 16), &bar[0]);
     }
-    if (v > 0 && player >= 0) v = ((v - (player + 1) + P) % P) + 1;      // CyTronGrid.pyx:65-71
-    board[idx] = (int8_t)v;
-    if (c < P) {
-        TronHdr s;
-        tron_hdr_decode(s, st[(long long)12 * B + e]);
-        int src = player >= 0 ? (c + player) % P : c;                    // py:392
-        if (heads) heads[e * P + c] = tron_sel4(s.hy, src) * N + tron_sel4(s.hx, src);
-        if (dirs) dirs[e * P + c] = tron_sel4(s.dir, src);
-        if (deaths) deaths[e * P + c] = tron_sel4(s.death, src);
-        if (terminal && c == 0) terminal[e] = (uint8_t)s.terminal;
+    __syncthreads();
+    mbar_wait(&bar[0], 0);
+#else
+    for (int v = 0; v < TRON_VEC; v++)
+        if ((int)threadIdx.x < n) tile.v[v][threadIdx.x] = st[(long long)v * B + e0 + threadIdx.x];
+    __syncthreads();
+#endif
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nview = ALL ? P : 1, chunks = (NN + 127) >> 7;
+    uint32_t lut_lo[4], lut_hi[4];
+#pragma unroll
+    for (int pv = 0; pv < 4; pv++) tron_view_lut(ALL ? pv : player, P, lut_lo[pv], lut_hi[pv]);
+    // lane l owns cells 128 k + 4 l .. + 3: word 4 k + (l >> 3) of every plane, bits (4 l & 31) .. + 3
+    const int sh = (4 * lane) & 31, wl = lane >> 3;
+    for (int t = warp; t < n; t += 4) {
+        const uint32_t *wp = tile.words(t) + wl;
+        uint8_t *out = img + t * nview * NN + 4 * lane;
+        for (int k = 0; k < chunks; k++, wp += TRON_OBS_TILE * 4, out += 128) {
+            uint32_t ow = 0;                                 // owner of the lane's 4 cells, one byte each
+#pragma unroll
+            for (int q = 0; q < 4; q++) ow += ((((wp[q * PL] >> sh) & 15u) * 0x00204081u) & TRON_ONES) * (uint32_t)(q + 1);
+            const uint32_t sel = __byte_perm(ow | ow >> 4, 0u, 0x4420);      // the 4 owners as PRMT selector nibbles
+            const int c0 = 128 * k + 4 * lane;
+            const bool guard = k == chunks - 1;
+            if (ALL) {
+#pragma unroll
+                for (int pv = 0; pv < 4; pv++)
+                    if (pv < P) tron_obs_store4(out + pv * NN, __byte_perm(lut_lo[pv], lut_hi[pv], sel), c0, NN, guard);
+            } else {
+                tron_obs_store4(out, __byte_perm(lut_lo[0], lut_hi[0], sel), c0, NN, guard);
+            }
+        }
+        if (lane < nview * P) {                                            // per-player vectors, rolled by the viewer (py:392-396)
+            const long long e = e0 + t;
+            const int pv = ALL ? lane / P : max(player, 0), c = ALL ? lane - pv * P : lane;
+            const uint4 h = tile.v[12][t];
+            const int src = (!ALL && player == -1) ? c : (c + pv) % P;
+            const uint32_t bx = (h.x >> (8 * src)) & 255u, by = (h.y >> (8 * src)) & 255u;
+            const long long o = (e * nview + (ALL ? pv : 0)) * P + c;
+            if (heads) heads[o] = ((int)(by & 31u) - 1) * N + (int)(bx & 31u) - 1;
+            if (dirs) dirs[o] = (int)(bx >> 5) & 3;
+            if (deaths) deaths[o] = (int)(by >> 5);
+            if (terminal && lane == 0) terminal[e] = (uint8_t)((h.z >> 27) & 1u);
+        }
     }
+    // the tile's boards: one bulk copy when the segment is 16-byte aligned and sized, a cooperative byte copy otherwise
+    const int nbytes = n * nview * NN;
+    int8_t *dst = board + e0 * nview * NN;
+#ifndef CRL_HOSTSIM
+    if ((nbytes & 15) == 0 && (((uintptr_t)dst) & 15) == 0) {
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(dst, img, (uint32_t)nbytes);
+            bulk_commit();
+            bulk_wait_read();
+        }
+        return;
+    }
+#endif
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = (int8_t)img[i];
 }
 
 // compute_ranking (TronGridEnvironment.py:483-508) of an arbitrary state, without stepping it: ranking byte per

@@ -266,28 +266,42 @@ __global__ void ttt_valid_kernel(const uint4 *__restrict__ st, uint32_t *__restr
     mask[e] = ~(v.x | v.y | v.z | v.w) & prm.cellmask;
 }
 
-// state_to_observation (2p :382-407): one thread per cell.  player < 0: absolute.  mod = 2 (2p) or 3 (3p AND 4p,
-// tictactoe_4p_env.py:50).  board int8[B][cells] (-1 empty); winner int8[B] (-1 None); mover int8[B].
-__global__ void ttt_observe_kernel(const uint4 *__restrict__ st, long long B, TTTParams prm, int player,
-                                   int8_t *__restrict__ board, int8_t *__restrict__ winner, int8_t *__restrict__ mover) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B * prm.cells) return;
-    long long e = idx / prm.cells;
-    int c = (int)(idx - e * prm.cells);
+// state_to_observation (2p :382-407).  A warp unpacks 32 environments: their `cells` * 32 output bytes are contiguous, so
+// in pass k lane l produces byte 32 k + l (environment (32 k + l) / cells of the warp, fetched with shuffles) and every
+// store instruction writes 32 consecutive bytes.  player == -1: absolute; -2: each game seen by its current mover
+// (CRL_PLAYER_MOVER).  mod = 2 (2p) or 3 (3p AND 4p, tictactoe_4p_env.py:50).
+// board int8[B][cells] (-1 empty); winner int8[B] (-1 None); mover int8[B].
+__global__ void __launch_bounds__(256)
+ttt_observe_kernel(const uint4 *__restrict__ st, long long B, TTTParams prm, int player,
+                   int8_t *__restrict__ board, int8_t *__restrict__ winner, int8_t *__restrict__ mover) {
+    const int lane = threadIdx.x & 31;
+    const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll;      // first environment of the warp
+    if (e0 >= B) return;
+    const long long e = e0 + lane;
     TTTEnv s;
-    ttt_decode(s, st[e]);
-    if (player == -2) player = s.mover;                     // CRL_PLAYER_MOVER: the game's current mover
-    int v = -1;
-#pragma unroll
-    for (int p = 0; p < 4; p++) v = (s.m[p] >> c & 1) ? p : v;
-    if (v >= 0 && player >= 0) {
-        int mod = prm.n == 2 ? 2 : 3;
-        v = (((v - player) % mod) + mod) % mod;
-    }
-    board[idx] = (int8_t)v;
-    if (c == 0) {
+    ttt_new_state(s);
+    if (e < B) {
+        ttt_decode(s, ld_stream(st + e));
         if (winner) winner[e] = (int8_t)(s.winner1 - 1);
         if (mover) mover[e] = (int8_t)s.mover;
+    }
+    const int cells = prm.cells, mod = prm.n == 2 ? 2 : 3;
+    const uint32_t magic = (65536u + (uint32_t)cells - 1u) / (uint32_t)cells;                 // exact b / cells for b < 32 * cells
+    const int nbytes = (int)min(32ll, B - e0) * cells;
+    for (int k = 0; k < cells; k++) {
+        const int b = 32 * k + lane;
+        const int el = (int)(((uint32_t)b * magic) >> 16), c = b - el * cells;
+        const uint32_t m0 = __shfl_sync(0xffffffffu, s.m[0], el), m1 = __shfl_sync(0xffffffffu, s.m[1], el);
+        const uint32_t m2 = __shfl_sync(0xffffffffu, s.m[2], el), m3 = __shfl_sync(0xffffffffu, s.m[3], el);
+        const int viewer = player == -2 ? __shfl_sync(0xffffffffu, s.mover, el) : player;
+        int v = -1;
+        v = (m0 >> c & 1u) ? 0 : v; v = (m1 >> c & 1u) ? 1 : v; v = (m2 >> c & 1u) ? 2 : v; v = (m3 >> c & 1u) ? 3 : v;
+        if (v >= 0 && viewer >= 0) {
+            v -= viewer;                                    // (v - viewer) mod `mod`, result in 0..mod-1
+            v = v % mod;
+            v += v < 0 ? mod : 0;
+        }
+        if (b < nbytes) board[e0 * cells + b] = (int8_t)v;
     }
 }
 

@@ -132,10 +132,12 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         return ((rk[:, None] >> shifts[None]) & 3).to(torch.uint8)
 
     def state_to_observation(self, state: TronBatchState, player: int) -> Dict[str, torch.Tensor]:
-        """TronGridEnvironment.state_to_observation (:363-405); player = -1 gives the absolute (unrotated) state."""
+        """TronGridEnvironment.state_to_observation (:363-405); player = -1 gives the absolute (unrotated) state,
+        player = -3 the views of ALL players in one pass: board [B, P, N, N], vectors [B, P, P]."""
         B, N, P = self.batch, self.N, self.num_players
-        board = torch.empty((B, N, N), dtype=torch.int8, device=self.device)
-        heads, dirs, deaths = (torch.empty((B, P), dtype=torch.int32, device=self.device) for _ in range(3))
+        views = (P,) if player == -3 else ()
+        board = torch.empty((B,) + views + (N, N), dtype=torch.int8, device=self.device)
+        heads, dirs, deaths = (torch.empty((B,) + views + (P,), dtype=torch.int32, device=self.device) for _ in range(3))
         self._check(self._lib.crl_tron_observe(state.packed.data_ptr(), int(player), board.data_ptr(), heads.data_ptr(),
                                                dirs.data_ptr(), deaths.data_ptr(), None, B, N, P, self._stream))
         return {"board": board, "heads": heads, "directions": dirs, "deaths": deaths}

@@ -32,8 +32,7 @@ class VectorEnv:
 
     def _observe(self) -> Dict[str, torch.Tensor]:
         if self.simultaneous:
-            per_seat = [self.env.state_to_observation(self.state, p) for p in range(self.num_players)]
-            return {k: torch.stack([o[k] for o in per_seat], dim=1) for k in per_seat[0]}
+            return self.env.state_to_observation(self.state, -3)      # CRL_PLAYER_ALL: every seat in one launch
         return self.env.state_to_observation(self.state, -2)          # CRL_PLAYER_MOVER
 
     def reset(self) -> Dict[str, torch.Tensor]:

@@ -31,6 +31,7 @@ extern "C" {
 
 #define CRL_PLAYER_ABSOLUTE (-1) /* observe: plain unpack, no perspective transform */
 #define CRL_PLAYER_MOVER (-2)    /* observe (Blokus, Tic Tac Toe): each game from the perspective of its current mover */
+#define CRL_PLAYER_ALL (-3)      /* observe (Tron): the views of all players at once */
 
 #define CRL_FLAG_AUTO_RESET 1 /* an environment whose stored terminal flag is set is replaced by new_state() before the step */
 
@@ -85,8 +86,10 @@ int crl_tron_policy_random(int8_t *actions, uint64_t seed, uint64_t first_env, u
 /* K fused random-policy steps with auto-reset, state kept in registers (identical to K x policy+step) */
 int crl_tron_rollout(void *state, uint8_t *result_or_null, int64_t *stats_or_null, uint64_t seed,
                      uint64_t first_env, uint32_t step0, int K, int64_t B, int N, int P, crl_stream_t stream);
-/* state_to_observation (TronGridEnvironment.py:363-405, CyTronGrid.pyx:65-71). player < 0: absolute unpack.
- * board int8[B][N][N]; heads (y*N+x) / directions / deaths int32[B][P] (may be NULL); terminal u8[B] (may be NULL) */
+/* state_to_observation (TronGridEnvironment.py:363-405, CyTronGrid.pyx:65-71). player = CRL_PLAYER_ABSOLUTE: plain
+ * unpack; player = CRL_PLAYER_ALL: the views of all P players in one pass (nview = P, else nview = 1).
+ * board int8[B][nview][N][N]; heads (y*N+x) / directions / deaths int32[B][nview][P] (may be NULL); terminal u8[B]
+ * (may be NULL) */
 int crl_tron_observe(const void *state, int player, int8_t *board, int32_t *heads, int32_t *directions,
                      int32_t *deaths, uint8_t *terminal_or_null, int64_t B, int N, int P, crl_stream_t stream);
 /* compute_ranking (TronGridEnvironment.py:483-508) of any state, without stepping it: ranking u8[B], 2 bits per

@@ -107,6 +107,15 @@ def case_golden_steps(be, path):
         sel = np.arange(len(idx)) * P + p
         assert (ob == g["obs_board"][sel]).all() and (oh == g["obs_heads"][sel]).all()
         assert (od == g["obs_directions"][sel]).all() and (ode == g["obs_deaths"][sel]).all()
+    # all views in one pass (CRL_PLAYER_ALL)
+    n = len(idx)
+    ab = be.zeros((n, P, N, N), np.int8)
+    ah, ad, ade = (be.zeros((n, P, P), np.int32) for _ in range(3))
+    be.check(be.lib.crl_tron_observe(be.ptr(sub), -3, be.ptr(ab), be.ptr(ah), be.ptr(ad), be.ptr(ade), None, n, N, P, be.stream))
+    assert (be.download(ab).reshape(n * P, N, N) == g["obs_board"]).all()
+    assert (be.download(ah).reshape(n * P, P) == g["obs_heads"]).all()
+    assert (be.download(ad).reshape(n * P, P) == g["obs_directions"]).all()
+    assert (be.download(ade).reshape(n * P, P) == g["obs_deaths"]).all()
 
 
 def case_adversarial(be):

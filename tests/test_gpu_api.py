@@ -124,5 +124,23 @@ def test_host_stepper_matches_next_state():
         sa, pa, ra, ta, wa = a_env.next_state(sa, None, a)
         stepper.actions.copy_(a)
         res = stepper()
-        assert res.is_pinned() and (res == sa.result.cpu()).all()
+        assert stepper.result.is_pinned() and (res == sa.result.cpu().numpy()).all()
     assert (sa.packed == sb.packed).all()
+    # a second stepper on its own stream, pipelined with the first (two independent batches in flight)
+    c_env = BatchedTronGridEnvironment("", batch=B, seed=3)
+    sc, _ = c_env.new_state()
+    side = torch.cuda.Stream()
+    stepper2 = c_env.host_stepper(sc, stream=side)
+    ref = BatchedTronGridEnvironment("", batch=B, seed=3)
+    sr, _ = ref.new_state()
+    sr, *_ = ref.next_state(sr, None, torch.zeros((B, 4), dtype=torch.int8))
+    for t in range(6):
+        a = rng.randint(-1, 2, size=(B, 4)).astype(np.int8)
+        stepper.actions_np[...] = a
+        stepper2.actions_np[...] = a
+        stepper.launch(); stepper2.launch()
+        sr, *_ = ref.next_state(sr, None, torch.from_numpy(a))
+        r1, r2 = stepper.wait().copy(), stepper2.wait().copy()
+        assert (r2 == sr.result.cpu().numpy()).all() and r1.shape == r2.shape
+    torch.cuda.synchronize()
+    assert (sc.packed == sr.packed).all()
