@@ -54,7 +54,8 @@ struct BlkSmem {
                                      // FIT_s[a - cell] a plain load + shift for every anchor a and shape cell.
                                      // Slots 0..27: the shapes of <= 4 cells; slots 28..35: the shapes of the ONE
                                      // pentomino piece being processed (5-cell shapes have no children)
-    uint16_t alist[BLK_MAX_ANCHORS + 4]; // anchors, row-major: y << 8 | (x + 4), then four padding entries
+    uint16_t ay[BLK_MAX_ANCHORS + 4];    // anchors, row-major: row y ...
+    uint16_t ax[BLK_MAX_ANCHORS + 4];    // ... and column x; then four padding entries (column 24: outside every FIT board)
 };
 
 __device__ __forceinline__ void blk_load(BlkSmem &sm, const uint4 *__restrict__ st, long long g, int lane) {
@@ -77,7 +78,7 @@ __device__ __forceinline__ void blk_new_state(BlkSmem &sm, int lane) {
     __syncwarp();
 }
 
-// A and ANC rows of player c (0-based) for the board in sm.st; fills sm.A, sm.anc, sm.alist; returns #anchors.
+// A and ANC rows of player c (0-based) for the board in sm.st; fills sm.A, sm.anc, sm.ay / sm.ax; returns #anchors.
 __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int round, int lane) {
     __syncwarp();
     uint32_t a = 0, an = 0;
@@ -110,9 +111,10 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
     while (an) {
         int x = __ffs((int)an) - 1;
         an &= an - 1;
-        sm.alist[pos++] = (uint16_t)(lane << 8 | (x + 4));
+        sm.ay[pos] = (uint16_t)lane;
+        sm.ax[pos++] = (uint16_t)x;
     }
-    if (lane < 4) sm.alist[total + lane] = 28;       // padding: "anchors" whose column lies outside every FIT board
+    if (lane < 4) { sm.ay[total + lane] = 0; sm.ax[total + lane] = 24; }   // padding: never fits
     __syncwarp();
     return total;
 }
@@ -272,10 +274,12 @@ __device__ __forceinline__ int blk_enumerate(BlkSmem &sm, int c, int round, uint
         const int sl0 = s0 + soff, sl1 = s1 + soff;
         const bool v0 = lane < nid && (nep >> (s0 - foff) & 1u), v1 = pent && (nep >> (s1 - foff) & 1u);
         if (__ballot_sync(0xffffffffu, v0 || v1) == 0u) continue;
+        // FIT_s[anchor - (dx, dy)] lives at bit (x - dx + 4) of row y - dy + 4: with the row shifted right by the
+        // (warp-uniform) anchor column the lane's test is one AND against its own constant mask 1 << (4 - dx)
         const uint32_t *f0 = sm.F + sl0 * BLK_FROWS + 4 - (int)((e0 >> 10) & 7u);
         const uint32_t *f1 = sm.F + sl1 * BLK_FROWS + 4 - (int)((e1 >> 10) & 7u);
-        const int xs0 = (int)((e0 >> 7) & 7u), xs1 = (int)((e1 >> 7) & 7u);
-        const int ok0 = (int)(e0 >> 13), ok1 = (int)(e1 >> 13);
+        const uint32_t k0 = v0 ? 1u << (4 - (int)((e0 >> 7) & 7u)) : 0u, k1 = v1 ? 1u << (4 - (int)((e1 >> 7) & 7u)) : 0u;
+        const int ok0 = (int)(e0 >> 13) + p * 16000, ok1 = (int)(e1 >> 13) + p * 16000;
         // ids 32..39 of a pentomino ("pass B") are tested for the next four anchors at once every fourth iteration
         const int j1 = lane >> 3;
         const uint32_t lt8 = (1u << (lane & 7)) - 1u;
@@ -283,17 +287,16 @@ __device__ __forceinline__ int blk_enumerate(BlkSmem &sm, int c, int round, uint
         bool hit1 = false;
         for (int ai = 0; ai < na; ai++) {
             const int sub = ai & 3;
-            if (pent && sub == 0) {
-                const int a1 = sm.alist[ai + j1];                        // (the list is padded with never-fitting anchors)
-                hit1 = v1 && ((f1[a1 >> 8] >> ((a1 & 255) - xs1)) & 1u);
+            if (pent && sub == 0) {                                      // (the list is padded with never-fitting anchors)
+                hit1 = ((f1[sm.ay[ai + j1]] >> sm.ax[ai + j1]) & k1) != 0u;
                 mB = __ballot_sync(0xffffffffu, hit1);
             }
-            const int a = sm.alist[ai], ay = a >> 8, ax4 = a & 255;
-            const bool hit = v0 && ((f0[ay] >> (ax4 - xs0)) & 1u);
+            const int ay = sm.ay[ai], ax = sm.ax[ai];
+            const bool hit = ((f0[ay] >> ax) & k0) != 0u;
             const uint32_t m = __ballot_sync(0xffffffffu, hit);
             const uint32_t mh = (mB >> (8 * sub)) & 255u;
             if ((m | mh) == 0u) continue;
-            const int code = (p * 400 + ay * 20 + ax4 - 4) * 40;
+            const int code = (ay * 20 + ax) * 40;
             int pos = base + __popc(m & lt);
             if (hit && pos < cap) out[pos] = code + ok0;                 // anchor ai: ids 0..31 ...
             base += __popc(m);
