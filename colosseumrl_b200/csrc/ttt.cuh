@@ -105,13 +105,20 @@ __device__ __forceinline__ uint32_t ttt_pack_result(const TTTOut &o) {
            (uint32_t)o.winners << 16 | rank << 24;
 }
 
-// Episode statistics of one step: 15 counters packed into 4 words -> 4 redux.sync per warp; lane 0 adds the
-// packed warp sums into per-warp shared slots (plain stores, one slot per warp) that are unpacked once per CTA.
-struct TTTStatAcc {
-    uint32_t a, b, c, d;   // running packed sums of this warp (lane 0 only)
-};
+// Episode statistics of one step: 15 counters packed into 4 words -> 4 redux.sync per warp; lane l < 15 then extracts
+// counter l from the (warp-uniform) sums and adds it to the CTA's shared partial -- ONE atomic instruction per warp.
+//   lane constants: word (0..3) | shift << 4 | bits << 10 | slot << 16
+#define TTT_SL(word, shift, bits, slot) ((word) | (shift) << 4 | (bits) << 10 | (slot) << 16)
+__constant__ uint32_t TTT_STAT_LANE[32] = {
+    TTT_SL(0, 0, 8, ST_STEPS), TTT_SL(0, 8, 8, ST_EPISODES), TTT_SL(0, 16, 8, ST_NOWIN), TTT_SL(0, 24, 8, ST_ERRORS),
+    TTT_SL(1, 0, 8, ST_WINS + 0), TTT_SL(1, 8, 8, ST_WINS + 1), TTT_SL(1, 16, 8, ST_WINS + 2), TTT_SL(1, 24, 8, ST_WINS + 3),
+    TTT_SL(2, 0, 8, ST_RANK + 0), TTT_SL(2, 8, 8, ST_RANK + 1), TTT_SL(2, 16, 8, ST_RANK + 2), TTT_SL(2, 24, 8, ST_RANK + 3),
+    TTT_SL(3, 0, 10, ST_NVALID), TTT_SL(3, 10, 10, ST_EPLEN), TTT_SL(3, 20, 12, ST_REWARD),
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define TTT_STAT_LANES 15
+
 template <int NP>
-__device__ __forceinline__ void ttt_stats(TTTStatAcc &acc, bool valid, const TTTOut &o, int mover, uint32_t ep_len) {
+__device__ __forceinline__ void ttt_stats(int *sm_stat, bool valid, const TTTOut &o, int mover, uint32_t ep_len, uint32_t lane_const) {
     const uint32_t t = (valid && o.terminal) ? 1u : 0u;
     const uint32_t w = t ? (uint32_t)o.winners : 0u, r = t ? (((1u << NP) - 1u) & ~(uint32_t)o.winners) : 0u;
     // fields hold sums over <= 32 lanes: 8-bit fields for 0/1 values, wider ones where needed
@@ -122,26 +129,13 @@ __device__ __forceinline__ void ttt_stats(TTTStatAcc &acc, bool valid, const TTT
                  (uint32_t)((valid ? (mover + 1) * o.reward : 0) + 4) << 20;           // reward biased by +4 per lane
     A = __reduce_add_sync(0xffffffffu, A); Bw = __reduce_add_sync(0xffffffffu, Bw);
     C = __reduce_add_sync(0xffffffffu, C); D = __reduce_add_sync(0xffffffffu, D);
-    acc.a = A; acc.b = Bw; acc.c = C; acc.d = D;
-}
-// add one step's packed warp sums into the CTA's shared counters (lane 0 of each warp)
-__device__ __forceinline__ void ttt_stats_commit(int *sm_stat, const TTTStatAcc &acc) {
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sm_stat[ST_STEPS], (int)(acc.a & 255u));
-        atomicAdd(&sm_stat[ST_NVALID], (int)(acc.d & 1023u));
-        atomicAdd(&sm_stat[ST_REWARD], (int)(acc.d >> 20) - 4 * 32);
-        if (acc.a >> 24) atomicAdd(&sm_stat[ST_ERRORS], (int)(acc.a >> 24));
-        if (acc.a >> 8 & 255u) {
-            atomicAdd(&sm_stat[ST_EPISODES], (int)(acc.a >> 8 & 255u));
-            atomicAdd(&sm_stat[ST_NOWIN], (int)(acc.a >> 16 & 255u));
-            atomicAdd(&sm_stat[ST_EPLEN], (int)(acc.d >> 10 & 1023u));
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                atomicAdd(&sm_stat[ST_WINS + p], (int)(acc.b >> (8 * p) & 255u));
-                atomicAdd(&sm_stat[ST_RANK + p], (int)(acc.c >> (8 * p) & 255u));
-            }
-        }
-    }
+    const uint32_t word = lane_const & 15u;
+    const uint32_t x = (A & -(uint32_t)(word == 0u)) | (Bw & -(uint32_t)(word == 1u)) | (C & -(uint32_t)(word == 2u)) |
+                       (D & -(uint32_t)(word == 3u));
+    int val = (int)((x >> ((lane_const >> 4) & 31u)) & ((1u << ((lane_const >> 10) & 31u)) - 1u));
+    const int slot = (int)(lane_const >> 16);
+    if (slot == ST_REWARD) val -= 4 * 32;
+    if ((int)(threadIdx.x & 31) < TTT_STAT_LANES && val != 0) atomicAdd(&sm_stat[slot], val);
 }
 
 __device__ __forceinline__ void ttt_zero_out(TTTOut &o) {
@@ -173,9 +167,7 @@ ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int
         if (valid_after) valid_after[e] = o.valid_after;
     }
     if (stats) {
-        TTTStatAcc acc;
-        ttt_stats<NP>(acc, valid, o, mover, ep_len);
-        ttt_stats_commit(sm_stat, acc);
+        ttt_stats<NP>(sm_stat, valid, o, mover, ep_len, TTT_STAT_LANE[threadIdx.x & 31]);
         __syncthreads();
         stats_flush_row(sm_stat, stats);
     }
@@ -228,6 +220,7 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
     ttt_zero_out(o);
     ttt_new_state(s);
     if (valid) ttt_decode(s, ld_stream(state + e));
+    const uint32_t lane_const = TTT_STAT_LANE[threadIdx.x & 31];
     for (int k = 0; k < K; k++) {
         int mover = 0;
         if (valid) {
@@ -236,11 +229,7 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
             mover = s.mover;
             ttt_step_env<NP>(s, ttt_random_action<NP>(s, r.x), o);
         }
-        if (stats) {
-            TTTStatAcc acc;
-            ttt_stats<NP>(acc, valid, o, mover, s.ep_len);
-            ttt_stats_commit(sm_stat, acc);
-        }
+        if (stats) ttt_stats<NP>(sm_stat, valid, o, mover, s.ep_len, lane_const);
     }
     if (valid) {
         st_stream(state + e, ttt_encode(s));
