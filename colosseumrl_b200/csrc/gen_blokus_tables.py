@@ -48,12 +48,16 @@ ROT = [
 ]
 
 
+ORIENTS = []             # (piece, orientation, shape, cells in shift order k)
+
+
 def build():
     shapes = []          # list of (piece, tuple(sorted cells))
     shape_index = {}
     piece_shape0 = []
     piece_id0 = []
     ids = []             # (shape, dx, dy, o*5+k)
+    ORIENTS.clear()
     for p, (_, offs) in enumerate(PIECES):
         piece_shape0.append(len(shapes))
         piece_id0.append(len(ids))
@@ -66,6 +70,7 @@ def build():
                 shape_index[key] = len(shapes)
                 shapes.append(key)
             s = shape_index[key]
+            ORIENTS.append((p, o, s, list(norm)))
             for k, (dx, dy) in enumerate(norm):
                 ids.append((s, dx, dy, o * 5 + k))
     piece_shape0.append(len(shapes))
@@ -178,6 +183,16 @@ def emit(path):
         cl = list(cells) + [cells[0]] * (5 - len(cells))
         L.append("    Y(%d, %d, %d, %d, %s) \\" % (i, pc, i - piece_shape0[pc], len(cells), ", ".join(str(dx | dy << 3) for dx, dy in cl)))
     L.append("")
+    L.append("// Per piece: its 8 orientations with the cells in shift order: Z(o, s, local, n, c0..c4), c = dx | dy << 3 = the")
+    L.append("// shape cell that sits on the anchor for shift k (id = o * n + k).  Expanded into straight-line tests.")
+    for pc in range(len(PIECES)):
+        L.append("#define BLK_ORIENTS_P%d(Z) \\" % pc)
+        for (p2, o, s_, cells) in ORIENTS:
+            if p2 != pc:
+                continue
+            cl = list(cells) + [cells[0]] * (5 - len(cells))
+            L.append("    Z(%d, %d, %d, %d, %s) \\" % (o, s_, s_ - piece_shape0[pc], len(cells), ", ".join(str(dx | dy << 3) for dx, dy in cl)))
+        L.append("")
     open(path, "w").write("\n".join(L) + "\n")
 
 
