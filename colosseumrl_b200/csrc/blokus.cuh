@@ -26,10 +26,16 @@
 // lanes = the (o, k) ids of one piece and __ballot_sync / __popc prefix sums for the compaction.
 //
 // FIT boards: the 91 oriented shapes are exactly the fixed polyominoes of 1..5 cells, so each is a smaller one plus
-// a cell and FIT_s[q] = FIT_parent[q + off] & A[q + c]: all boards a player needs cost <= 90 AND steps (lanes = rows),
-// generated as straight-line code from blokus_tables.h (every offset an immediate).  Shapes whose pieces are not held
-// or whose parent fits nowhere are skipped.  The any-move test of the terminal check needs no anchor loop at all:
-// piece p has a move  <=>  OR_s OR_k (ANC & shift(FIT_s, cell_k)) != 0, evaluated level by level with an early exit.
+// a cell and FIT_s[q] = FIT_parent[q + off] & A[q + c].  The tree is evaluated level by level with LANES = SHAPES:
+// each lane builds the 20 rows of its own shape's board (2 LDS, 2 shifts, 1 AND, 1 STS per row, parameters from a
+// per-shape table) and one ballot per pass yields the non-empty flags of up to 32 shapes: 3 passes for the shapes
+// of 2..4 cells, then one pass per group of pentomino pieces (the groups share the same slots; a group is built,
+// its pieces are emitted, the next group overwrites it).  Shapes whose pieces are not held or whose parent fits
+// nowhere are idle lanes; a pass without work is skipped.  Everything is a compact loop: the first version was
+// 86 KB of straight-line SASS and spent 70 % of its cycles waiting for the instruction cache.
+// The any-move test of the terminal check needs no anchor loop at all:
+// piece p has a move  <=>  OR_s OR_k (ANC & shift(FIT_s, cell_k)) != 0, again with lanes = shapes, level by level
+// with an early exit.
 #pragma once
 #include "crl_common.cuh"
 #include "philox.cuh"
@@ -37,25 +43,26 @@
 
 #define BLK_WORDS 88
 #define BLK_VEC 22
-#define BLK_WARPS 4            // warps (= games) per CTA
+#define BLK_WARPS 1            // legal / step: ONE warp (= game) per CTA, so the game index is blockIdx.x and every
+                               // vote / shuffle sits in provably uniform control flow (no BRA.DIV slow paths)
+#define BLK_OBS_WARPS 4        // observation kernel: games per CTA
 #define BLK_ROWMASK 0xFFFFFu
 #define BLK_MAX_ANCHORS 400
 
-#define BLK_FROWS 24           // rows of a FIT board: y = -4..19 at index y + 4 (rows -4..-1 are zero)
-#define BLK_FSLOTS (BLK_NSHAPE_LE4 + 8)
-#define BLK_SLOT(s, local) ((s) < BLK_NSHAPE_LE4 ? (s) : BLK_NSHAPE_LE4 + (local))
+#define BLK_FSLOTS (BLK_NSHAPE_LE4 + BLK_GROUP_MAX)
 
 // per-warp shared scratch
 struct BlkSmem {
     uint32_t st[BLK_WORDS];          // the game state (old board during a step)
-    uint32_t A[24];                  // allowed rows; rows 20..23 are zero (shapes are at most 5 rows tall)
-    uint32_t anc[20];                // anchor rows
-    uint32_t F[BLK_FSLOTS * BLK_FROWS];   // FIT boards: bit (x + 4) of word [slot * 24 + y + 4]; the padding makes
-                                     // FIT_s[a - cell] a plain load + shift for every anchor a and shape cell.
-                                     // Slots 0..27: the shapes of <= 4 cells; slots 28..35: the shapes of the ONE
-                                     // pentomino piece being processed (5-cell shapes have no children)
-    uint16_t ay[BLK_MAX_ANCHORS + 4];    // anchors, row-major: row y ...
-    uint16_t ax[BLK_MAX_ANCHORS + 4];    // ... and column x; then four padding entries (column 24: outside every FIT board)
+    uint32_t A[24];                  // allowed rows << 4 (bit x + 4); rows 20..23 are zero (shapes are at most 5 rows tall)
+    uint32_t anc[20];                // anchor rows (bit x)
+    alignas(16) uint32_t F[BLK_FSLOTS * BLK_FROWS + 3];   // FIT boards: bit (x + 4) of word [slot * BLK_FROWS + y + 4];
+                                     // the zero padding (rows -4..-1, 20..24, bits 0..3) makes FIT_s[a - cell] a plain
+                                     // load + shift for every anchor a and shape cell, and a tree step branch-free
+    // anchors, row-major, one word each: (4 * y) << 25 | x, then >= 4 padding entries (column 24: outside every FIT
+    // board).  The low 5 bits feed a wrap-mode funnel shift directly, the top 7 are the byte offset of FIT row y.
+    alignas(16) uint32_t anch[BLK_MAX_ANCHORS + 8];
+    uint16_t acode[BLK_MAX_ANCHORS + 8];  // (y * 20 + x) * 40: the anchor's part of the action id
 };
 
 __device__ __forceinline__ void blk_load(BlkSmem &sm, const uint4 *__restrict__ st, long long g, int lane) {
@@ -78,7 +85,9 @@ __device__ __forceinline__ void blk_new_state(BlkSmem &sm, int lane) {
     __syncwarp();
 }
 
-// A and ANC rows of player c (0-based) for the board in sm.st; fills sm.A, sm.anc, sm.ay / sm.ax; returns #anchors.
+// A and ANC rows of player c (0-based) for the board in sm.st; fills sm.A, sm.anc and (LIST) the row-major anchor
+// list sm.anch / sm.acode; returns #anchors.
+template <bool LIST>
 __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int round, int lane) {
     __syncwarp();
     uint32_t a = 0, an = 0;
@@ -97,7 +106,7 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
             an = a & d4;
         }
     }
-    if (lane < 24) sm.A[lane] = a;
+    if (lane < 24) sm.A[lane] = a << 4;
     if (lane < 20) sm.anc[lane] = an;
     // row-major anchor list: exclusive prefix of the per-row counts
     int cnt = __popc(an), pre = cnt;
@@ -106,204 +115,211 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
         int t = __shfl_up_sync(0xffffffffu, pre, d);
         if (lane >= d) pre += t;
     }
-    int total = __shfl_sync(0xffffffffu, pre, 31);
-    int pos = pre - cnt;
-    while (an) {
-        int x = __ffs((int)an) - 1;
-        an &= an - 1;
-        sm.ay[pos] = (uint16_t)lane;
-        sm.ax[pos++] = (uint16_t)x;
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    if (LIST) {
+        int pos = pre - cnt;
+        while (an) {
+            const int x = __ffs((int)an) - 1;
+            an &= an - 1;
+            sm.anch[pos] = (uint32_t)(4 * lane) << 25 | (uint32_t)x;
+            sm.acode[pos++] = (uint16_t)((lane * 20 + x) * 40);
+        }
+        if (lane < 4) { sm.anch[total + lane] = 24u; sm.acode[total + lane] = 0; }   // padding: never fits
     }
-    if (lane < 4) { sm.ay[total + lane] = 0; sm.ax[total + lane] = 24; }   // padding: never fits
     __syncwarp();
     return total;
 }
 
-// ---- FIT boards through the polyomino tree -----------------------------------------------------------------
-// ne = bit s set iff FIT_s (s < 28) has been built and is not empty; ne5 = the same for the 8 slots of the
-// current pentomino piece (both warp-uniform)
-
-// shape 0 (the monomino): FIT = A
-__device__ __forceinline__ uint32_t blk_tree_root(BlkSmem &sm, int lane, int frow) {
-    const uint32_t f = lane < 20 ? sm.A[lane] << 4 : 0u;
-    if (lane < BLK_FROWS) sm.F[frow] = f;
-    return __any_sync(0xffffffffu, f != 0u) ? 1u : 0u;
+// ---- FIT boards through the polyomino tree, lanes = shapes ---------------------------------------------------
+// zero every board once per kernel (the passes only write rows 0..19 of the boards they build)
+__device__ __forceinline__ void blk_zero_fit(BlkSmem &sm, int lane) {
+    uint4 *f4 = (uint4 *)sm.F;
+    for (int i = lane; i < (BLK_FSLOTS * BLK_FROWS + 3) / 4; i += 32) f4[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// one tree step; every argument except sm / ne / lane / frow is a literal
-#define BLK_TREE_STEP(s, local, par, px, py, cx, cy, nevar)                                                   \
-    if (ne >> (par) & 1u) {                                                                                   \
-        uint32_t f_ = 0u;                                                                                     \
-        if (lane < 20 - (py)) f_ = (sm.F[(par) * BLK_FROWS + 4 + (py) + lane] >> (px)) & ((sm.A[lane + (cy)] >> (cx)) << 4); \
-        if (lane < BLK_FROWS) sm.F[BLK_SLOT(s, local) * BLK_FROWS + frow] = f_;                                 \
-        if (__any_sync(0xffffffffu, f_ != 0u)) nevar |= 1u << ((s) < BLK_NSHAPE_LE4 ? (s) : (local));          \
-    }
-
-// the shapes with LEVEL (2..4) cells that some held piece needs
-template <int LEVEL>
-__device__ __forceinline__ void blk_tree_level(BlkSmem &sm, uint32_t &ne, uint32_t inv, int lane, int frow) {
-#define BLK_X(level, s, piece, local, par, px, py, cx, cy, need) \
-    if ((level) == LEVEL && (inv & (need))) BLK_TREE_STEP(s, local, par, px, py, cx, cy, ne)
-    BLK_TREE_LIST(BLK_X)
-#undef BLK_X
+// shape 0 (the monomino): FIT = A.  Returns its non-empty flag.
+__device__ __forceinline__ uint32_t blk_tree_root(BlkSmem &sm, int lane) {
+    const uint32_t f = lane < 20 ? sm.A[lane] : 0u;
+    if (lane < 20) sm.F[4 + lane] = f;
+    const uint32_t ne = __any_sync(0xffffffffu, f != 0u) ? 1u : 0u;
     __syncwarp();
+    return ne;
 }
 
-// the (<= 8) shapes of pentomino piece PIECE into slots 28..35; returns their non-empty flags
-template <int PIECE>
-__device__ __forceinline__ uint32_t blk_tree_pentomino(BlkSmem &sm, uint32_t ne, int lane, int frow) {
-    uint32_t ne5 = 0u;
-#define BLK_X(level, s, piece, local, par, px, py, cx, cy, need) \
-    if ((level) == 5 && (piece) == PIECE) BLK_TREE_STEP(s, local, par, px, py, cx, cy, ne5)
-    BLK_TREE_LIST(BLK_X)
-#undef BLK_X
+// One pass: lane l builds FIT of shape s0 + l (if s0 + l < s1, a held piece needs it and its parent is non-empty).
+// Returns the ballot of the non-empty boards (bit l = shape s0 + l).
+__device__ __forceinline__ uint32_t blk_tree_pass(BlkSmem &sm, int s0, int s1, uint32_t ne, uint32_t inv, int lane) {
+    const uint4 t = BLK_SHAPE_TAB_G[s0 + lane];
+    const bool active = s0 + lane < s1 && (inv & t.y) != 0u && (ne >> (t.y >> 24) & 1u) != 0u;
+    if (!__any_sync(0xffffffffu, active)) return 0u;
+    uint32_t acc = 0u;
+    if (active) {
+        const char *pp = (const char *)sm.F + (t.x & 0xffffu);      // parent row 4 + py
+        const char *pa = (const char *)sm.A + (t.x >> 24);          // A row cy
+        char *po = (char *)sm.F + (t.w & 0xffffu);                  // own row 4
+        const uint32_t px = t.x >> 16, cx = t.x >> 20;              // wrap-mode shifts use the low 5 bits: px, cx <= 4
+#pragma unroll 5
+        for (int r = 0; r < 20; r++) {
+            const uint32_t f = __funnelshift_r(*(const uint32_t *)(pp + 4 * r), 0u, px & 7u) &
+                               __funnelshift_r(*(const uint32_t *)(pa + 4 * r), 0u, cx & 7u) & 0xfffffff0u;
+            *(uint32_t *)(po + 4 * r) = f;
+            acc |= f;
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, acc != 0u);
     __syncwarp();
-    return ne5;
+    return m;
 }
 
-__device__ __forceinline__ uint32_t blk_tree_pentomino_dyn(BlkSmem &sm, int p, uint32_t ne, int lane, int frow) {
-    __syncwarp();                // the previous piece's readers are done with slots 28..35
-    switch (p) {
-    case 9: return blk_tree_pentomino<9>(sm, ne, lane, frow);
-    case 10: return blk_tree_pentomino<10>(sm, ne, lane, frow);
-    case 11: return blk_tree_pentomino<11>(sm, ne, lane, frow);
-    case 12: return blk_tree_pentomino<12>(sm, ne, lane, frow);
-    case 13: return blk_tree_pentomino<13>(sm, ne, lane, frow);
-    case 14: return blk_tree_pentomino<14>(sm, ne, lane, frow);
-    case 15: return blk_tree_pentomino<15>(sm, ne, lane, frow);
-    case 16: return blk_tree_pentomino<16>(sm, ne, lane, frow);
-    case 17: return blk_tree_pentomino<17>(sm, ne, lane, frow);
-    case 18: return blk_tree_pentomino<18>(sm, ne, lane, frow);
-    case 19: return blk_tree_pentomino<19>(sm, ne, lane, frow);
-    default: return blk_tree_pentomino<20>(sm, ne, lane, frow);
-    }
+// the shapes with `level` (2..4) cells
+__device__ __forceinline__ void blk_tree_level(BlkSmem &sm, uint32_t &ne, uint32_t inv, int level, int lane) {
+    const int s0 = BLK_LEVEL_S0[level - 1];
+    ne |= blk_tree_pass(sm, s0, BLK_LEVEL_S0[level], ne, inv, lane) << s0;
 }
 
-// any-move test: OR_k (ANC & shift(FIT_s, cell_k)) over the shapes selected by COND
-#define BLK_ANY_CELL(slot, c) (sm.F[(slot) * BLK_FROWS + 4 + lane - ((c) >> 3)] >> (4 - ((c) & 7)))
-#define BLK_ANY_STEP(s, local, n, c0, c1, c2, c3, c4, nevar)                                                  \
-    if (nevar >> ((s) < BLK_NSHAPE_LE4 ? (s) : (local)) & 1u) {                                               \
-        if (lane < 20) {                                                                                      \
-            uint32_t d_ = BLK_ANY_CELL(BLK_SLOT(s, local), c0);                                               \
-            if ((n) > 1) d_ |= BLK_ANY_CELL(BLK_SLOT(s, local), c1);                                          \
-            if ((n) > 2) d_ |= BLK_ANY_CELL(BLK_SLOT(s, local), c2);                                          \
-            if ((n) > 3) d_ |= BLK_ANY_CELL(BLK_SLOT(s, local), c3);                                          \
-            if ((n) > 4) d_ |= BLK_ANY_CELL(BLK_SLOT(s, local), c4);                                          \
-            acc |= d_ & anc;                                                                                  \
-        }                                                                                                     \
-    }
+// the shapes of pentomino group g into slots 28..; returns their non-empty flags (bit = shape - group start)
+__device__ __forceinline__ uint32_t blk_tree_group(BlkSmem &sm, int g, uint32_t ne, uint32_t inv, int lane) {
+    __syncwarp();                // the previous group's readers are done with the shared slots
+    return blk_tree_pass(sm, BLK_GROUP_S0[g], BLK_GROUP_S0[g + 1], ne, inv, lane);
+}
 
-// held pieces with LEVEL (1..4) cells
-template <int LEVEL>
-__device__ __forceinline__ bool blk_any_level(BlkSmem &sm, uint32_t ne, uint32_t inv, uint32_t anc, int lane) {
+// any-move test, lanes = the shapes [s0, s1): does a held piece have a placement of one of these shapes that covers
+// an anchor?  flags: bit l = FIT of shape s0 + l is non-empty.
+__device__ __forceinline__ bool blk_any_pass(BlkSmem &sm, int s0, int s1, uint32_t flags, uint32_t inv, int lane) {
+    const uint4 t = BLK_SHAPE_TAB_G[s0 + lane];
+    const bool active = s0 + lane < s1 && (inv >> (t.w >> 16 & 31u) & 1u) != 0u && (flags >> lane & 1u) != 0u;
+    if (!__any_sync(0xffffffffu, active)) return false;
     uint32_t acc = 0u;
-#define BLK_Y(s, piece, local, n, c0, c1, c2, c3, c4) \
-    if ((n) == LEVEL && (inv >> (piece) & 1u)) BLK_ANY_STEP(s, local, n, c0, c1, c2, c3, c4, ne)
-    BLK_SHAPE_LIST(BLK_Y)
-#undef BLK_Y
-    return __any_sync(0xffffffffu, acc != 0u);
-}
-
-template <int PIECE>
-__device__ __forceinline__ bool blk_any_pentomino(BlkSmem &sm, uint32_t ne, uint32_t anc, int lane, int frow) {
-    const uint32_t ne5 = blk_tree_pentomino<PIECE>(sm, ne, lane, frow);
-    uint32_t acc = 0u;
-#define BLK_Y(s, piece, local, n, c0, c1, c2, c3, c4) \
-    if ((n) == 5 && (piece) == PIECE) BLK_ANY_STEP(s, local, n, c0, c1, c2, c3, c4, ne5)
-    BLK_SHAPE_LIST(BLK_Y)
-#undef BLK_Y
-    return __any_sync(0xffffffffu, acc != 0u);
+    if (active) {
+        const int n = (int)(t.w >> 24);
+        const char *po = (const char *)sm.F + (t.w & 0xffffu);
+        uint32_t cells = t.z;
+#pragma unroll 1
+        for (int k = 0; k < n; k++, cells >>= 6) {                  // OR_k shift(FIT_s, cell_k) & ANC, row by row
+            const char *pk = po - 4 * (int)(cells >> 3 & 7u);
+            const uint32_t sh = 4u - (cells & 7u);
+#pragma unroll 5
+            for (int r = 0; r < 20; r++) acc |= __funnelshift_r(*(const uint32_t *)(pk + 4 * r), 0u, sh) & sm.anc[r];
+        }
+    }
+    return __any_sync(0xffffffffu, acc != 0u) != 0;
 }
 
 // AI.check_moves (ai.py:36-42): does player c holding `inv` have any move on the board in sm.st?
 __device__ __forceinline__ int blk_any_move(BlkSmem &sm, int c, int round, uint32_t inv, int lane) {
-    if (inv == 0u || blk_allowed_and_anchors(sm, c, round, lane) == 0) return 0;
-    const uint32_t anc = lane < 20 ? sm.anc[lane] : 0u;
-    const int frow = lane < 20 ? lane + 4 : lane - 20;
-    uint32_t ne = blk_tree_root(sm, lane, frow);
-    __syncwarp();
-    if (blk_any_level<1>(sm, ne, inv, anc, lane)) return 1;
-    blk_tree_level<2>(sm, ne, inv, lane, frow);
-    if (blk_any_level<2>(sm, ne, inv, anc, lane)) return 1;
-    blk_tree_level<3>(sm, ne, inv, lane, frow);
-    if (blk_any_level<3>(sm, ne, inv, anc, lane)) return 1;
-    blk_tree_level<4>(sm, ne, inv, lane, frow);
-    if (blk_any_level<4>(sm, ne, inv, anc, lane)) return 1;
-#define BLK_P5(P)                                                                            \
-    if (inv >> (P) & 1u) {                                                                   \
-        __syncwarp();                                                                        \
-        if (blk_any_pentomino<P>(sm, ne, anc, lane, frow)) return 1;                         \
+    inv = __reduce_or_sync(0xffffffffu, inv);
+    if (inv == 0u || blk_allowed_and_anchors<false>(sm, c, round, lane) == 0) return 0;
+    if (inv & 1u) return 1;                                  // the monomino fits on every anchor (ANC is a subset of A)
+    uint32_t ne = blk_tree_root(sm, lane);
+#pragma unroll 1
+    for (int level = 2; level <= 4; level++) {
+        blk_tree_level(sm, ne, inv, level, lane);
+        const int s0 = BLK_LEVEL_S0[level - 1];
+        if (blk_any_pass(sm, s0, BLK_LEVEL_S0[level], ne >> s0, inv, lane)) return 1;
     }
-    BLK_P5(9) BLK_P5(10) BLK_P5(11) BLK_P5(12) BLK_P5(13) BLK_P5(14)
-    BLK_P5(15) BLK_P5(16) BLK_P5(17) BLK_P5(18) BLK_P5(19) BLK_P5(20)
-#undef BLK_P5
+#pragma unroll 1
+    for (int g = 0; g < BLK_NGROUP; g++) {
+        const uint32_t ne5 = blk_tree_group(sm, g, ne, inv, lane);
+        if (ne5 != 0u && blk_any_pass(sm, BLK_GROUP_S0[g], BLK_GROUP_S0[g + 1], ne5, inv, lane)) return 1;
+    }
     return 0;
+}
+
+// ---- emission ---------------------------------------------------------------------------------------------------
+// One held piece p, anchors in groups of four.  Lanes = (anchor a = lane >> 3 of the group, orientation o = lane & 7);
+// a lane tests the piece's <= 5 shifts k for its (anchor, orientation):
+//   FIT_s[anchor - cell_k]  =  bit (x + 4 - dx_k) of row (y + 4 - dy_k) of the orientation's board
+// = one address add, one LDS, one add, one wrap-mode shift (the anchor word's low bits are the column) and one funnel
+// shift that pushes the hit bit into the lane's accumulator: no vote, no branch.  The accumulator ends up with one
+// byte per group (5 hit bits), so ONE SWAR popcount and ONE shuffle scan position all hits of up to 16 anchors:
+// lane order (a, o) followed by k IS the reference's order (anchor row-major -> orientation -> shift), and the action
+// id is anchor code + piece * 16000 + o * 5 + k.  Each lane then stores its own <= 5 ids of a group.
+template <bool PENT>
+__device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int p, int na, int lane, int base,
+                                              int32_t *__restrict__ out, int cap) {
+    // nemask: the non-empty flags the piece's table entries index (`ne`, or its pentomino group's `ne5`)
+    const int n = PENT ? 5 : (int)BLK_PIECE_SIZE[p];
+    const int o = lane & 7, a = lane >> 3;
+    const uint16_t *e = BLK_ORIENT_TAB_G[p * 8 + o];
+    const bool v = (nemask >> e[10] & 1u) != 0u;
+    if (!__any_sync(0xffffffffu, v)) return base;            // none of the piece's shapes fits anywhere
+    const char *fb = (const char *)sm.F;
+    const uint32_t f0 = e[0], f1 = e[1], f2 = e[2], f3 = e[3], f4 = e[4];          // row offsets, bytes
+    const uint32_t c0 = e[5], c1 = e[6], c2 = e[7], c3 = e[8], c4 = e[9];          // column constants
+    const int val00 = p * 16000 + o * 5;
+#define BLK_TEST(fk, ck) hh = __funnelshift_r(hh, __funnelshift_r(*(const uint32_t *)(fb + ((fk) + row)), 0u, w + (ck)), 1)
+#pragma unroll 1
+    for (int a0 = 0; a0 < na; a0 += 16) {                    // chunks of four groups (one or two chunks in practice)
+        const int ng = min(4, (na - a0 + 3) >> 2);
+        uint32_t hh = 0u;
+#pragma unroll 1
+        for (int g = 0; g < ng; g++) {
+            const uint32_t w = sm.anch[a0 + 4 * g + a];      // (the list is padded with never-fitting anchors)
+            const uint32_t row = w >> 25;
+            BLK_TEST(f0, c0);
+            if (n > 1) BLK_TEST(f1, c1);
+            if (n > 2) BLK_TEST(f2, c2);
+            if (n > 3) BLK_TEST(f3, c3);
+            if (n > 4) BLK_TEST(f4, c4);
+            hh >>= 8 - n;                                    // one byte per group
+        }
+        hh = v ? hh >> (8 * (4 - ng)) : 0u;                  // byte g = hits of (anchor a0 + 4 g + a, o), bit k = shift k
+        if (!__any_sync(0xffffffffu, hh != 0u)) continue;
+        uint32_t cc = hh - ((hh >> 1) & 0x55555555u);        // per-byte popcount
+        cc = (cc & 0x33333333u) + ((cc >> 2) & 0x33333333u);
+        cc = (cc + (cc >> 4)) & 0x0f0f0f0fu;
+        uint32_t incl = cc;                                  // per-byte inclusive scan over the lanes (sums <= 160)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31), excl = incl - cc;
+        const bool careful = base + (int)((tot * 0x01010101u) >> 24) > cap;        // rare: the caller's list is too short
+#pragma unroll 1
+        for (int g = 0; g < ng; g++) {
+            const uint32_t sel = 0x4440u + (uint32_t)g;      // byte g, zero-extended
+            uint32_t h = __byte_perm(hh, 0u, sel);
+            int pos = base + (int)__byte_perm(excl, 0u, sel);
+            base += (int)__byte_perm(tot, 0u, sel);
+            if (careful)                                     // drop the ids that do not fit (the count stays complete)
+                while (h != 0u && __popc(h) > max(cap - pos, 0)) h &= ~(0x80000000u >> __clz((int)h));
+            const int val0 = (int)sm.acode[a0 + 4 * g + a] + val00;
+            int32_t *q = out + pos;
+            if (h & 1u) st_global_u32(q++, val0);
+            if (h & 2u) st_global_u32(q++, val0 + 1);
+            if (h & 4u) st_global_u32(q++, val0 + 2);
+            if (h & 8u) st_global_u32(q++, val0 + 3);
+            if (h & 16u) st_global_u32(q, val0 + 4);
+        }
+    }
+#undef BLK_TEST
+    return base;
 }
 
 // Enumerate the legal moves of player c holding `inv` on the board in sm.st: action ids in the reference's order
 // into out[0..cap), returns the full count.
 __device__ __forceinline__ int blk_enumerate(BlkSmem &sm, int c, int round, uint32_t inv, int lane,
                                              int32_t *__restrict__ out, int cap) {
-    const int na = blk_allowed_and_anchors(sm, c, round, lane);
+    inv = __reduce_or_sync(0xffffffffu, inv);                // same in every lane
+    const int na = blk_allowed_and_anchors<true>(sm, c, round, lane);
     if (na == 0 || inv == 0u) return 0;
-    const int frow = lane < 20 ? lane + 4 : lane - 20;
-    uint32_t ne = blk_tree_root(sm, lane, frow);
-    __syncwarp();
-    blk_tree_level<2>(sm, ne, inv, lane, frow);
-    blk_tree_level<3>(sm, ne, inv, lane, frow);
-    blk_tree_level<4>(sm, ne, inv, lane, frow);
+    uint32_t ne = blk_tree_root(sm, lane);
+    blk_tree_level(sm, ne, inv, 2, lane);
+    blk_tree_level(sm, ne, inv, 3, lane);
+    blk_tree_level(sm, ne, inv, 4, lane);
     int base = 0;
-    const uint32_t lt = (1u << lane) - 1u;
-    for (int p = 0; p < BLK_NPIECE; p++) {
-        if (!(inv >> p & 1u)) continue;
-        const int id0 = BLK_PIECE_ID0[p], nid = BLK_PIECE_ID0[p + 1] - id0, sh0 = BLK_PIECE_SHAPE0[p];
-        const bool pent = nid > 32;                                      // 40 ids: the 12 pentominoes
-        uint32_t nep = ne;                                               // non-empty flags of shape s: bit s - foff
-        int soff = 0, foff = 0;
-        if (pent) {
-            nep = blk_tree_pentomino_dyn(sm, p, ne, lane, frow);
-            if (nep == 0u) continue;                                     // none of the piece's shapes fits anywhere
-            soff = BLK_NSHAPE_LE4 - sh0;                                 // shape s of this piece lives in slot s + soff
-            foff = sh0;
-        }
-        // lane = (orientation, shift) id of the piece: its shape's FIT board, the cell that sits on the anchor.
-        // A pentomino's ids 32..39 are tested for FOUR anchors per pass: lane = (anchor j = lane >> 3, id 32 + (lane & 7)).
-        const uint32_t e0 = lane < nid ? BLK_ID_TAB_G[id0 + lane] : 0u;
-        const uint32_t e1 = pent ? BLK_ID_TAB_G[id0 + 32 + (lane & 7)] : 0u;
-        const int s0 = lane < nid ? (int)(e0 & 127u) : foff, s1 = pent ? (int)(e1 & 127u) : foff;
-        const int sl0 = s0 + soff, sl1 = s1 + soff;
-        const bool v0 = lane < nid && (nep >> (s0 - foff) & 1u), v1 = pent && (nep >> (s1 - foff) & 1u);
-        if (__ballot_sync(0xffffffffu, v0 || v1) == 0u) continue;
-        // FIT_s[anchor - (dx, dy)] lives at bit (x - dx + 4) of row y - dy + 4: with the row shifted right by the
-        // (warp-uniform) anchor column the lane's test is one AND against its own constant mask 1 << (4 - dx)
-        const uint32_t *f0 = sm.F + sl0 * BLK_FROWS + 4 - (int)((e0 >> 10) & 7u);
-        const uint32_t *f1 = sm.F + sl1 * BLK_FROWS + 4 - (int)((e1 >> 10) & 7u);
-        const uint32_t k0 = v0 ? 1u << (4 - (int)((e0 >> 7) & 7u)) : 0u, k1 = v1 ? 1u << (4 - (int)((e1 >> 7) & 7u)) : 0u;
-        const int ok0 = (int)(e0 >> 13) + p * 16000, ok1 = (int)(e1 >> 13) + p * 16000;
-        // ids 32..39 of a pentomino ("pass B") are tested for the next four anchors at once every fourth iteration
-        const int j1 = lane >> 3;
-        const uint32_t lt8 = (1u << (lane & 7)) - 1u;
-        uint32_t mB = 0u;
-        bool hit1 = false;
-        for (int ai = 0; ai < na; ai++) {
-            const int sub = ai & 3;
-            if (pent && sub == 0) {                                      // (the list is padded with never-fitting anchors)
-                hit1 = ((f1[sm.ay[ai + j1]] >> sm.ax[ai + j1]) & k1) != 0u;
-                mB = __ballot_sync(0xffffffffu, hit1);
-            }
-            const int ay = sm.ay[ai], ax = sm.ax[ai];
-            const bool hit = ((f0[ay] >> ax) & k0) != 0u;
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            const uint32_t mh = (mB >> (8 * sub)) & 255u;
-            if ((m | mh) == 0u) continue;
-            const int code = (ay * 20 + ax) * 40;
-            int pos = base + __popc(m & lt);
-            if (hit && pos < cap) out[pos] = code + ok0;                 // anchor ai: ids 0..31 ...
-            base += __popc(m);
-            pos = base + __popc(mh & lt8);
-            if (hit1 && j1 == sub && pos < cap) out[pos] = code + ok1;   // ... then ids 32..39
-            base += __popc(mh);
-        }
+#pragma unroll 1
+    for (uint32_t rest = inv & ((1u << BLK_GROUP_P0[0]) - 1u); rest; rest &= rest - 1u)      // pieces of <= 4 cells
+        base = blk_emit_piece<false>(sm, ne, __ffs((int)rest) - 1, na, lane, base, out, cap);
+#pragma unroll 1
+    for (int g = 0; g < BLK_NGROUP; g++) {                                                   // pentominoes, group by group
+        uint32_t rest = inv & ((1u << BLK_GROUP_P0[g + 1]) - (1u << BLK_GROUP_P0[g]));
+        if (rest == 0u) continue;
+        const uint32_t ne5 = blk_tree_group(sm, g, ne, inv, lane);
+        if (ne5 == 0u) continue;
+#pragma unroll 1
+        for (; rest; rest &= rest - 1u) base = blk_emit_piece<true>(sm, ne5, __ffs((int)rest) - 1, na, lane, base, out, cap);
     }
     return base;
 }
@@ -316,15 +332,20 @@ blokus_legal_kernel(const uint4 *__restrict__ st, int32_t *__restrict__ counts, 
     __shared__ int sm_stat[CRL_NSTAT];
     BlockStats bs{sm_stat};
     if (stats) bs.init();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = BLK_WARPS == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31), wid = BLK_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
     const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
     if (g < B) {
         BlkSmem &sm = smem[wid];
+        blk_zero_fit(sm, lane);
         blk_load(sm, st, g, lane);
         if ((flags & CRL_FLAG_AUTO_RESET) && (sm.st[85] >> 16 & 1u)) blk_new_state(sm, lane);
         const uint32_t meta = sm.st[85];
         const int c = player >= 0 ? player : (int)(meta >> 8 & 3u);
-        const int n = blk_enumerate(sm, c, (int)(meta & 0xffu), sm.st[80 + c], lane, ids + g * cap, cap);
+        int32_t *out = ids + g * cap;
+#ifndef CRL_HOSTSIM
+        asm volatile("" : "+l"(out));         // keep the game's list base in one register pair: a store is IMAD.WIDE + STG
+#endif
+        const int n = blk_enumerate(sm, c, (int)(meta & 0xffu), sm.st[80 + c], lane, out, cap);
         if (lane == 0) {
             counts[g] = n;
             if (stats) atomicAdd(&sm_stat[ST_NVALID], n);
@@ -343,10 +364,11 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
     __shared__ int sm_stat[CRL_NSTAT];
     BlockStats bs{sm_stat};
     if (stats) bs.init();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = BLK_WARPS == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31), wid = BLK_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
     const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
     if (g < B) {
         BlkSmem &sm = smem[wid];
+        blk_zero_fit(sm, lane);
         blk_load(sm, in, g, lane);
         if ((flags & CRL_FLAG_AUTO_RESET) && (sm.st[85] >> 16 & 1u)) blk_new_state(sm, lane);
         const uint32_t meta = sm.st[85];
@@ -370,7 +392,7 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
             const uint32_t cells = BLK_SHAPE_CELLS[e & 127u];
             const int ay = cell / 20, ax = cell - ay * 20;
             const int qx = ax - (int)((e >> 7) & 7u), qy = ay - (int)((e >> 10) & 7u);
-            blk_allowed_and_anchors(sm, mover, round, lane);      // validation against A / ANC of the mover
+            blk_allowed_and_anchors<false>(sm, mover, round, lane);      // validation against A / ANC of the mover
             legal = legal && qx >= 0 && qy >= 0 && (sm.anc[ay] >> ax & 1u);
             uint32_t add = 0;
 #pragma unroll
@@ -378,7 +400,7 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
                 const uint32_t cd = cells >> (6 * i);
                 const int x = qx + (int)(cd & 7u), y = qy + (int)((cd >> 3) & 7u);
                 // y <= 23 by construction (rows 20..23 of A are zero), x may exceed 19 -> bit not in A
-                legal = legal && x >= 0 && y >= 0 && x < 20 && (sm.A[min(max(y, 0), 23)] >> max(x, 0) & 1u);
+                legal = legal && x >= 0 && y >= 0 && x < 20 && (sm.A[min(max(y, 0), 23)] >> (max(x, 0) + 4) & 1u);
                 add |= (y == lane && x >= 0 && x < 20) ? (1u << x) : 0u;
             }
             if (legal) {
@@ -488,12 +510,12 @@ __global__ void blokus_reset_kernel(uint4 *__restrict__ st, const uint8_t *__res
 //  player == -1: absolute unpack: board = Board.board_contents (0 empty, 1..4 colour), pieces / score in seat order.
 //  player == -2: like player >= 0 with every game seen by its own current mover (CRL_PLAYER_MOVER).
 //  meta (optional) int32[B][4] = round, mover, terminal, episode steps.
-__global__ void __launch_bounds__(32 * BLK_WARPS)
+__global__ void __launch_bounds__(32 * BLK_OBS_WARPS)
 blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, int8_t *__restrict__ board,
                       uint8_t *__restrict__ pieces, int32_t *__restrict__ score, int32_t *__restrict__ meta) {
-    __shared__ uint32_t sst[BLK_WARPS][BLK_WORDS];
+    __shared__ uint32_t sst[BLK_OBS_WARPS][BLK_WORDS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
+    const long long g = (long long)blockIdx.x * BLK_OBS_WARPS + wid;
     if (g >= B) return;
     uint32_t *s = sst[wid];
     if (lane < BLK_VEC) {

@@ -501,7 +501,7 @@ int crl_blokus_observe(const void *state, int player, int8_t *board, uint8_t *pi
                        int64_t B, crl_stream_t stream) {
     if (!state || !board || !pieces || !score || B < 0 || player > 3 || player < -2) return fail(CRL_ERR_ARG, "crl_blokus_observe: bad argument%s");
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(blokus_observe_kernel, blocks_for(B, BLK_WARPS), 32 * BLK_WARPS, (cudaStream_t)stream, (const uint4 *)state,
+    CRL_LAUNCH(blokus_observe_kernel, blocks_for(B, BLK_OBS_WARPS), 32 * BLK_OBS_WARPS, (cudaStream_t)stream, (const uint4 *)state,
                (long long)B, player, board, pieces, score, meta);
     return check_launch("blokus_observe_kernel");
 }

@@ -67,6 +67,15 @@ __device__ __forceinline__ void st_stream(uint4 *p, uint4 v) {
 #endif
 }
 
+// plain 32-bit global store through a pointer whose address space the compiler can no longer infer
+__device__ __forceinline__ void st_global_u32(int32_t *p, int32_t v) {
+#ifndef CRL_HOSTSIM
+    asm volatile("st.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+
 // ---- bulk asynchronous copies (TMA 1-D, SASS UBLKCP) between global memory and a shared-memory tile ----------
 // The SoA state layout makes every 16-byte vector of a CTA's environments one contiguous global segment, so a
 // tile is moved by a handful of bulk copies issued by ONE thread; the other threads never touch the data they

@@ -158,41 +158,86 @@ def emit(path):
     for i in range(0, len(row), 8):
         L.append("    " + ", ".join(row[i:i + 8]) + ",")
     L.append("};")
-    L.append("// the same table in global memory for lane-indexed reads (a divergent __constant__ read is serialised)")
-    L.append("__device__ const uint32_t BLK_ID_TAB_G[BLK_NID] = {")
-    for i in range(0, len(row), 8):
-        L.append("    " + ", ".join(row[i:i + 8]) + ",")
-    L.append("};")
-    L.append("// Polyomino tree (see build_tree in the generator): X(level, s, piece, local, parent, px, py, cx, cy, need) for")
-    L.append("// s = 1..90 in shape order (= by size); FIT_s[q] = FIT_parent[q + (px, py)] & A[q + (cx, cy)]; local = s - first")
-    L.append("// shape of its piece; `need` = pieces that need s (own piece + descendants).  Expanded into straight-line code,")
-    L.append("// so every field is an immediate.  Shapes of 5 cells are leaves: need == 1 << piece.")
-    L.append("#define BLK_NSHAPE_LE4 %d" % sum(1 for _, c in shapes if len(c) <= 4))
-    L.append("#define BLK_TREE_LIST(X) \\")
-    for i in range(1, len(shapes)):
-        par, px, py, cx, cy = tree[i]
+    n_le4 = sum(1 for _, c in shapes if len(c) <= 4)
+    FROWS = 29
+    L.append("// ---- FIT-board storage: %d words per board (index y + 4: rows -4..-1 and 20..24 are zero; an odd stride spreads" % FROWS)
+    L.append("// the boards over the shared-memory banks when lanes = shapes).  Boards of the shapes of <= 4 cells live in slots")
+    L.append("// 0..%d; the pentomino shapes are processed in groups of whole pieces that share slots %d.. :" % (n_le4 - 1, n_le4))
+    L.append("#define BLK_FROWS %d" % FROWS)
+    L.append("#define BLK_NSHAPE_LE4 %d" % n_le4)
+    # greedy grouping of the pentomino pieces, at most 24 shapes per group
+    groups, cur = [], None
+    for pc in range(len(PIECES)):
+        if len(PIECES[pc][1]) < 5:
+            continue
+        nsh = piece_shape0[pc + 1] - piece_shape0[pc]
+        if cur is None or cur[3] + nsh > 24:
+            cur = [pc, pc + 1, piece_shape0[pc], nsh]
+            groups.append(cur)
+        else:
+            cur[1] = pc + 1
+            cur[3] += nsh
+    L.append("#define BLK_NGROUP %d" % len(groups))
+    L.append("#define BLK_GROUP_MAX %d" % max(g[3] for g in groups))
+    L.append("// group g: pieces [BLK_GROUP_P0[g], BLK_GROUP_P0[g+1]), shapes [BLK_GROUP_S0[g], BLK_GROUP_S0[g+1])")
+    L.append("__constant__ uint8_t BLK_GROUP_P0[BLK_NGROUP + 1] = {" + ", ".join(str(g[0]) for g in groups) + ", %d};" % len(PIECES))
+    L.append("__constant__ uint8_t BLK_GROUP_S0[BLK_NGROUP + 1] = {" + ", ".join(str(g[2]) for g in groups) + ", %d};" % len(shapes))
+    group_of = {}
+    for gi, g in enumerate(groups):
+        for pc in range(g[0], g[1]):
+            group_of[pc] = gi
+    L.append("// pentomino piece -> its group (pieces of <= 4 cells: 255)")
+    L.append("__constant__ uint8_t BLK_PIECE_GROUP[BLK_NPIECE] = {" + ", ".join(str(group_of.get(pc, 255)) for pc in range(len(PIECES))) + "};")
+    sizes = [len(c) for _, c in shapes]
+    lv = [sizes.index(k) for k in range(1, 6)] + [len(shapes)]
+    L.append("// shapes of k cells are [BLK_LEVEL_S0[k-1], BLK_LEVEL_S0[k])")
+    L.append("__constant__ uint8_t BLK_LEVEL_S0[6] = {" + ", ".join(map(str, lv)) + "};")
+
+    def slot_flag(i):
         pc = shapes[i][0]
         if len(shapes[i][1]) == 5:
-            assert need[i] == 1 << pc and len(shapes[par][1]) == 4
-        L.append("    X(%d, %d, %d, %d, %d, %d, %d, %d, %d, 0x%06xu) \\" % (len(shapes[i][1]), i, pc, i - piece_shape0[pc], par, px, py,
-                                                                       cx, cy, need[i]))
-    L.append("")
-    L.append("// Shapes with their cells: Y(s, piece, local, ncells, c0..c4) with c = dx | dy << 3 (unused cells repeat cell 0)")
-    L.append("#define BLK_SHAPE_LIST(Y) \\")
-    for i, (pc, cells) in enumerate(shapes):
+            g = groups[group_of[pc]]
+            return n_le4 + i - g[2], i - g[2]
+        return i, i
+
+    L.append("// per (piece, orientation), read by the lanes that own the orientation during emission, 12 x uint16, every field")
+    L.append("// directly usable (no unpacking):  [0..4] byte offset of FIT row (4 - dy_k) of the orientation's slot for shift")
+    L.append("// k = 0..4 (the shape cell (dx_k, dy_k) sits on the anchor; id = o * 5 + k), [5..9] 4 - dx_k, [10] non-empty flag")
+    L.append("// index (s for <= 4 cells: bit of `ne`; s - group start for pentominoes: bit of the group's `ne5`), [11] unused")
+    L.append("__device__ const uint16_t BLK_ORIENT_TAB_G[BLK_NPIECE * 8][12] = {")
+    for (pc, o, s_, cells) in ORIENTS:
+        slot, flag = slot_flag(s_)
         cl = list(cells) + [cells[0]] * (5 - len(cells))
-        L.append("    Y(%d, %d, %d, %d, %s) \\" % (i, pc, i - piece_shape0[pc], len(cells), ", ".join(str(dx | dy << 3) for dx, dy in cl)))
-    L.append("")
-    L.append("// Per piece: its 8 orientations with the cells in shift order: Z(o, s, local, n, c0..c4), c = dx | dy << 3 = the")
-    L.append("// shape cell that sits on the anchor for shift k (id = o * n + k).  Expanded into straight-line tests.")
-    for pc in range(len(PIECES)):
-        L.append("#define BLK_ORIENTS_P%d(Z) \\" % pc)
-        for (p2, o, s_, cells) in ORIENTS:
-            if p2 != pc:
-                continue
-            cl = list(cells) + [cells[0]] * (5 - len(cells))
-            L.append("    Z(%d, %d, %d, %d, %s) \\" % (o, s_, s_ - piece_shape0[pc], len(cells), ", ".join(str(dx | dy << 3) for dx, dy in cl)))
-        L.append("")
+        offs = [(slot * FROWS + 4 - dy) * 4 for dx, dy in cl]
+        cs = [4 - dx for dx, dy in cl]
+        L.append("    {" + ", ".join(str(v) for v in offs + cs + [flag, 0]) + "},")
+    L.append("};")
+    L.append("// Polyomino tree (see build_tree in the generator), one entry per shape, read by the lane that owns the shape")
+    L.append("// (lanes = shapes of one level / pentomino group):   FIT_s[q] = FIT_parent[q + (px, py)] & A[q + (cx, cy)]")
+    L.append("//  .x = byte offset of parent row (4 + py) | px << 16 | cx << 20 | (4 * cy) << 24")
+    L.append("//  .y = pieces that need s (own piece + descendants; 5-cell shapes are leaves) | parent's flag index << 24")
+    L.append("//  .z = the shape's cells, 5 x 6 bits (dx | dy << 3), short shapes repeat cell 0")
+    L.append("//  .w = byte offset of the shape's own row 4 (y = 0) | piece << 16 | cells << 24")
+    L.append("__device__ const uint4 BLK_SHAPE_TAB_G[BLK_NSHAPE + 5] = {")
+    for i in range(len(shapes)):
+        pc, cells = shapes[i]
+        slot, flag = slot_flag(i)
+        if i == 0:
+            par, px, py, cx, cy = 0, 0, 0, 0, 0
+        else:
+            par, px, py, cx, cy = tree[i]
+        assert len(shapes[par][1]) <= 4 and par < n_le4
+        cl = list(cells) + [cells[0]] * (5 - len(cells))
+        cw = 0
+        for k, (dx, dy) in enumerate(cl):
+            cw |= (dx | dy << 3) << (6 * k)
+        x = ((par * FROWS + 4 + py) * 4) | px << 16 | cx << 20 | (4 * cy) << 24
+        y = need[i] | par << 24
+        w = ((slot * FROWS + 4) * 4) | pc << 16 | len(cells) << 24
+        L.append("    {0x%08xu, 0x%08xu, 0x%08xu, 0x%08xu}," % (x, y, cw, w))
+    for _ in range(5):
+        L.append("    {0u, 0u, 0u, 0u},")
+    L.append("};")
     open(path, "w").write("\n".join(L) + "\n")
 
 

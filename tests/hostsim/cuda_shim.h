@@ -161,6 +161,12 @@ static inline unsigned __vminu2(unsigned a, unsigned b) {
     unsigned al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16, lo = al < bl ? al : bl, hi = ah < bh ? ah : bh;
     return lo | hi << 16;
 }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {   // shf.r.wrap.b32
+    return (unsigned)(((((uint64_t)hi) << 32) | lo) >> (sh & 31u));
+}
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) {   // shf.l.wrap.b32
+    return (unsigned)((((((uint64_t)hi) << 32) | lo) << (sh & 31u)) >> 32);
+}
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
