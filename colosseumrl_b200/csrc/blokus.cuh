@@ -56,13 +56,13 @@ struct BlkSmem {
     uint32_t st[BLK_WORDS];          // the game state (old board during a step)
     uint32_t A[24];                  // allowed rows << 4 (bit x + 4); rows 20..23 are zero (shapes are at most 5 rows tall)
     uint32_t anc[20];                // anchor rows (bit x)
-    alignas(16) uint32_t F[BLK_FSLOTS * BLK_FROWS + 3];   // FIT boards: bit (x + 4) of word [slot * BLK_FROWS + y + 4];
+    alignas(16) uint32_t F[BLK_FSLOTS * BLK_FROWS + 4];   // FIT boards: bit (x + 4) of word [slot * BLK_FROWS + y + 4];
                                      // the zero padding (rows -4..-1, 20..24, bits 0..3) makes FIT_s[a - cell] a plain
                                      // load + shift for every anchor a and shape cell, and a tree step branch-free
-    // anchors, row-major, one word each: (4 * y) << 25 | x, then >= 4 padding entries (column 24: outside every FIT
-    // board).  The low 5 bits feed a wrap-mode funnel shift directly, the top 7 are the byte offset of FIT row y.
-    alignas(16) uint32_t anch[BLK_MAX_ANCHORS + 8];
-    uint16_t acode[BLK_MAX_ANCHORS + 8];  // (y * 20 + x) * 40: the anchor's part of the action id
+    // anchors, row-major, 16 bits each: (4 * y) << 9 | x, then >= 4 padding entries (column 24: outside every FIT
+    // board).  One PRMT expands an entry to w = (4 * y) << 25 | x: the low 5 bits feed a wrap-mode funnel shift
+    // directly, the top 7 are the byte offset of FIT row y.
+    uint16_t anch[BLK_MAX_ANCHORS + 8];
 };
 
 __device__ __forceinline__ void blk_load(BlkSmem &sm, const uint4 *__restrict__ st, long long g, int lane) {
@@ -121,10 +121,9 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
         while (an) {
             const int x = __ffs((int)an) - 1;
             an &= an - 1;
-            sm.anch[pos] = (uint32_t)(4 * lane) << 25 | (uint32_t)x;
-            sm.acode[pos++] = (uint16_t)((lane * 20 + x) * 40);
+            sm.anch[pos++] = (uint16_t)((4 * lane) << 9 | x);
         }
-        if (lane < 4) { sm.anch[total + lane] = 24u; sm.acode[total + lane] = 0; }   // padding: never fits
+        if (lane < 4) sm.anch[total + lane] = 24;            // padding: never fits
     }
     __syncwarp();
     return total;
@@ -134,7 +133,7 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
 // zero every board once per kernel (the passes only write rows 0..19 of the boards they build)
 __device__ __forceinline__ void blk_zero_fit(BlkSmem &sm, int lane) {
     uint4 *f4 = (uint4 *)sm.F;
-    for (int i = lane; i < (BLK_FSLOTS * BLK_FROWS + 3) / 4; i += 32) f4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = lane; i < (BLK_FSLOTS * BLK_FROWS + 4) / 4; i += 32) f4[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // shape 0 (the monomino): FIT = A.  Returns its non-empty flag.
@@ -254,7 +253,7 @@ __device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int 
         uint32_t hh = 0u;
 #pragma unroll 1
         for (int g = 0; g < ng; g++) {
-            const uint32_t w = sm.anch[a0 + 4 * g + a];      // (the list is padded with never-fitting anchors)
+            const uint32_t w = __byte_perm(sm.anch[a0 + 4 * g + a], 0u, 0x1440u);   // (the list is padded with never-fitting anchors)
             const uint32_t row = w >> 25;
             BLK_TEST(f0, c0);
             if (n > 1) BLK_TEST(f1, c1);
@@ -284,7 +283,8 @@ __device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int 
             base += (int)__byte_perm(tot, 0u, sel);
             if (careful)                                     // drop the ids that do not fit (the count stays complete)
                 while (h != 0u && __popc(h) > max(cap - pos, 0)) h &= ~(0x80000000u >> __clz((int)h));
-            const int val0 = (int)sm.acode[a0 + 4 * g + a] + val00;
+            const uint32_t w = sm.anch[a0 + 4 * g + a];
+            const int val0 = (int)(w >> 9) * 200 + (int)(w & 31u) * 40 + val00;      // (y * 20 + x) * 40 + ...
             int32_t *q = out + pos;
             if (h & 1u) st_global_u32(q++, val0);
             if (h & 2u) st_global_u32(q++, val0 + 1);

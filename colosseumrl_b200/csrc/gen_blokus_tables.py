@@ -159,9 +159,10 @@ def emit(path):
         L.append("    " + ", ".join(row[i:i + 8]) + ",")
     L.append("};")
     n_le4 = sum(1 for _, c in shapes if len(c) <= 4)
-    FROWS = 29
-    L.append("// ---- FIT-board storage: %d words per board (index y + 4: rows -4..-1 and 20..24 are zero; an odd stride spreads" % FROWS)
-    L.append("// the boards over the shared-memory banks when lanes = shapes).  Boards of the shapes of <= 4 cells live in slots")
+    FROWS = 25
+    L.append("// ---- FIT-board storage: %d words per board (index y + 4: rows -4..-1 and 20 are zero, rows 21..23 are the next" % FROWS)
+    L.append("// board's zero rows -4..-2; the odd stride spreads the boards over the shared-memory banks when lanes = shapes).")
+    L.append("// Boards of the shapes of <= 4 cells live in slots")
     L.append("// 0..%d; the pentomino shapes are processed in groups of whole pieces that share slots %d.. :" % (n_le4 - 1, n_le4))
     L.append("#define BLK_FROWS %d" % FROWS)
     L.append("#define BLK_NSHAPE_LE4 %d" % n_le4)
