@@ -86,7 +86,7 @@ __device__ __forceinline__ void blk_new_state(BlkSmem &sm, int lane) {
 }
 
 // A and ANC rows of player c (0-based) for the board in sm.st; fills sm.A, sm.anc and (LIST) the row-major anchor
-// list sm.anch / sm.acode; returns #anchors.
+// list sm.anch and returns #anchors, or (!LIST) returns the mask of the rows that hold an anchor.
 template <bool LIST>
 __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int round, int lane) {
     __syncwarp();
@@ -108,6 +108,10 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
     }
     if (lane < 24) sm.A[lane] = a << 4;
     if (lane < 20) sm.anc[lane] = an;
+    if (!LIST) {                                             // callers only need "which rows hold an anchor"
+        __syncwarp();
+        return (int)__ballot_sync(0xffffffffu, an != 0u);
+    }
     // row-major anchor list: exclusive prefix of the per-row counts
     int cnt = __popc(an), pre = cnt;
 #pragma unroll
@@ -116,15 +120,13 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
         if (lane >= d) pre += t;
     }
     const int total = __shfl_sync(0xffffffffu, pre, 31);
-    if (LIST) {
-        int pos = pre - cnt;
-        while (an) {
-            const int x = __ffs((int)an) - 1;
-            an &= an - 1;
-            sm.anch[pos++] = (uint16_t)((4 * lane) << 9 | x);
-        }
-        if (lane < 4) sm.anch[total + lane] = 24;            // padding: never fits
+    int pos = pre - cnt;
+    while (an) {
+        const int x = __ffs((int)an) - 1;
+        an &= an - 1;
+        sm.anch[pos++] = (uint16_t)((4 * lane) << 9 | x);
     }
+    if (lane < 4) sm.anch[total + lane] = 24;                // padding: never fits
     __syncwarp();
     return total;
 }
@@ -182,44 +184,54 @@ __device__ __forceinline__ uint32_t blk_tree_group(BlkSmem &sm, int g, uint32_t 
     return blk_tree_pass(sm, BLK_GROUP_S0[g], BLK_GROUP_S0[g + 1], ne, inv, lane);
 }
 
-// any-move test, lanes = the shapes [s0, s1): does a held piece have a placement of one of these shapes that covers
-// an anchor?  flags: bit l = FIT of shape s0 + l is non-empty.
-__device__ __forceinline__ bool blk_any_pass(BlkSmem &sm, int s0, int s1, uint32_t flags, uint32_t inv, int lane) {
+// any-move test, lanes = the shapes [s0, s1) of n cells: does a held piece have a placement of one of these shapes
+// that covers an anchor?  flags: bit l = FIT of shape s0 + l is non-empty; rows = the board rows that hold an anchor.
+__device__ __forceinline__ bool blk_any_pass(BlkSmem &sm, int s0, int s1, int n, uint32_t flags, uint32_t inv, uint32_t rows,
+                                             int lane) {
     const uint4 t = BLK_SHAPE_TAB_G[s0 + lane];
     const bool active = s0 + lane < s1 && (inv >> (t.w >> 16 & 31u) & 1u) != 0u && (flags >> lane & 1u) != 0u;
     if (!__any_sync(0xffffffffu, active)) return false;
     uint32_t acc = 0u;
     if (active) {
-        const int n = (int)(t.w >> 24);
         const char *po = (const char *)sm.F + (t.w & 0xffffu);
-        uint32_t cells = t.z;
+        // OR_k shift(FIT_s, cell_k) & ANC on the anchor rows (short shapes repeat cell 0)
+        const char *p0 = po - 4 * (int)(t.z >> 3 & 7u), *p1 = po - 4 * (int)(t.z >> 9 & 7u), *p2 = po - 4 * (int)(t.z >> 15 & 7u);
+        const char *p3 = po - 4 * (int)(t.z >> 21 & 7u), *p4 = po - 4 * (int)(t.z >> 27 & 7u);
+        const uint32_t h0 = 4u - (t.z & 7u), h1 = 4u - (t.z >> 6 & 7u), h2 = 4u - (t.z >> 12 & 7u);
+        const uint32_t h3 = 4u - (t.z >> 18 & 7u), h4 = 4u - (t.z >> 24 & 7u);
 #pragma unroll 1
-        for (int k = 0; k < n; k++, cells >>= 6) {                  // OR_k shift(FIT_s, cell_k) & ANC, row by row
-            const char *pk = po - 4 * (int)(cells >> 3 & 7u);
-            const uint32_t sh = 4u - (cells & 7u);
-#pragma unroll 5
-            for (int r = 0; r < 20; r++) acc |= __funnelshift_r(*(const uint32_t *)(pk + 4 * r), 0u, sh) & sm.anc[r];
+        for (uint32_t rm = rows; rm; rm &= rm - 1u) {
+            const int r4 = 4 * (__ffs((int)rm) - 1);
+            uint32_t d = __funnelshift_r(*(const uint32_t *)(p0 + r4), 0u, h0) | __funnelshift_r(*(const uint32_t *)(p1 + r4), 0u, h1);
+            if (n > 2) d |= __funnelshift_r(*(const uint32_t *)(p2 + r4), 0u, h2);
+            if (n > 3) d |= __funnelshift_r(*(const uint32_t *)(p3 + r4), 0u, h3);
+            if (n > 4) d |= __funnelshift_r(*(const uint32_t *)(p4 + r4), 0u, h4);
+            acc |= d & *(const uint32_t *)((const char *)sm.anc + r4);
         }
     }
     return __any_sync(0xffffffffu, acc != 0u) != 0;
 }
 
 // AI.check_moves (ai.py:36-42): does player c holding `inv` have any move on the board in sm.st?
-__device__ __forceinline__ int blk_any_move(BlkSmem &sm, int c, int round, uint32_t inv, int lane) {
+__device__ __forceinline__ int blk_any_move(BlkSmem &sm, int c, int round, uint32_t inv, int lane, bool &zeroed) {
     inv = __reduce_or_sync(0xffffffffu, inv);
-    if (inv == 0u || blk_allowed_and_anchors<false>(sm, c, round, lane) == 0) return 0;
+    if (inv == 0u) return 0;
+    const uint32_t rows = (uint32_t)blk_allowed_and_anchors<false>(sm, c, round, lane);
+    if (rows == 0u) return 0;
     if (inv & 1u) return 1;                                  // the monomino fits on every anchor (ANC is a subset of A)
+    if (!zeroed) { blk_zero_fit(sm, lane); zeroed = true; __syncwarp(); }  // (the common case never gets here)
     uint32_t ne = blk_tree_root(sm, lane);
 #pragma unroll 1
     for (int level = 2; level <= 4; level++) {
         blk_tree_level(sm, ne, inv, level, lane);
         const int s0 = BLK_LEVEL_S0[level - 1];
-        if (blk_any_pass(sm, s0, BLK_LEVEL_S0[level], ne >> s0, inv, lane)) return 1;
+        if (blk_any_pass(sm, s0, BLK_LEVEL_S0[level], level, ne >> s0, inv, rows, lane)) return 1;
     }
 #pragma unroll 1
     for (int g = 0; g < BLK_NGROUP; g++) {
+        if (!(inv & ((1u << BLK_GROUP_P0[g + 1]) - (1u << BLK_GROUP_P0[g])))) continue;
         const uint32_t ne5 = blk_tree_group(sm, g, ne, inv, lane);
-        if (ne5 != 0u && blk_any_pass(sm, BLK_GROUP_S0[g], BLK_GROUP_S0[g + 1], ne5, inv, lane)) return 1;
+        if (ne5 != 0u && blk_any_pass(sm, BLK_GROUP_S0[g], BLK_GROUP_S0[g + 1], 5, ne5, inv, rows, lane)) return 1;
     }
     return 0;
 }
@@ -368,8 +380,8 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
     const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
     if (g < B) {
         BlkSmem &sm = smem[wid];
-        blk_zero_fit(sm, lane);
         blk_load(sm, in, g, lane);
+        bool zeroed = false;
         if ((flags & CRL_FLAG_AUTO_RESET) && (sm.st[85] >> 16 & 1u)) blk_new_state(sm, lane);
         const uint32_t meta = sm.st[85];
         const int round = (int)(meta & 0xffu), mover = (int)(meta >> 8 & 3u);
@@ -429,7 +441,7 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
             uint32_t iq = 0;
 #pragma unroll
             for (int r = 0; r < 4; r++) iq |= (r == q) ? inv[r] : 0u;
-            any = blk_any_move(sm, q, round, iq, lane);
+            any = blk_any_move(sm, q, round, iq, lane, zeroed);
         }
         const int terminal = !any;
         int reward = 0, winners = 0;
