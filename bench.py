@@ -361,18 +361,52 @@ def run_b200(args):
     for _ in range(max(W, G)):
         work.step(k); k += 1
     torch.cuda.synchronize()
-    work.prepare(k, K)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
+    S = max(1, min(args.streams, G))
     cap_stream = torch.cuda.Stream(dev)
-    saved_t = list(work.local_t)
-    with torch.cuda.graph(graph, stream=cap_stream):
-        for j in range(K):
-            work.step(k + j, slot=j)
-    torch.cuda.synchronize()
-    # (capture does not execute: the local step counters advanced, the states did not -- that is what replay does)
+    side = [torch.cuda.Stream(dev) for _ in range(S - 1)]
 
-    graph_upload(graph, stream)                    # keep the one-off upload of the executable graph out of the timing
+    def capture(k0, n, nstreams):
+        """n steps k0..k0+n-1 in one CUDA graph.  Steps of different replicas are independent (a replica's own steps
+        stay ordered: replica g always runs on chain g % nstreams), so with nstreams > 1 the graph has parallel chains
+        and the launch ramp / drain of one step overlaps the next replica's step."""
+        work.prepare(k0, n)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        lanes = [cap_stream] + side[:nstreams - 1]
+        with torch.cuda.graph(gr, stream=cap_stream):
+            fork = torch.cuda.Event()
+            fork.record(cap_stream)
+            for s_ in lanes[1:]:
+                s_.wait_event(fork)
+            for j in range(n):
+                with torch.cuda.stream(lanes[((k0 + j) % G) % nstreams]):
+                    work.step(k0 + j, slot=j)
+            for s_ in lanes[1:]:
+                join = torch.cuda.Event()
+                join.record(s_)
+                cap_stream.wait_event(join)
+        torch.cuda.synchronize()
+        # (capture does not execute: the local step counters advanced, the states did not -- that is what replay does)
+        graph_upload(gr, stream)               # keep the one-off upload of the executable graph out of the timing
+        torch.cuda.synchronize()
+        return gr
+
+    # for the report only (untimed as far as the contract goes, it doubles as warm-up): the same steps as ONE dependent
+    # chain, i.e. every launch waits for its predecessor
+    serial = None
+    if S > 1:
+        Ks = min(K, 400)
+        gs = capture(k, Ks, 1)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        gs.replay()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        serial = s0.elapsed_time(s1) / Ks
+        k += Ks
+        del gs
+    graph = capture(k, K, S)
+    work.stats_env.stats_rows.zero_()              # count the timed steps only
     torch.cuda.synchronize()
 
     clocks = ClockSampler(local)
@@ -442,11 +476,16 @@ def run_b200(args):
             "config": {"workload": wl["desc"], "batch_per_gpu": B, "policy": "philox4x32-10 uniform random, auto-reset",
                        "l2": "inputs larger than L2: %d independent replicas of the batch per GPU (%.0f MB of state) "
                              "stepped round-robin, no flush kernel" % (G, G * per_replica / 1e6),
-                       "launch": "K steps captured in one CUDA graph", "state_bytes_per_env": wl["state"],
+                       "launch": "K steps captured in one CUDA graph" + ("" if S == 1 else ", the independent replicas spread over %d parallel chains (a replica's own steps stay ordered)" % S),
+                       "chains": S, "state_bytes_per_env": wl["state"],
                        "parallelism": "env-sharded x%d, no data-path collective, 1 stats all-reduce" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": wl["kernel"],
-                         "algorithmic_bytes_per_env_step": bytes_per_step, "launch_ms": launch_ms},
+                         "algorithmic_bytes_per_env_step": bytes_per_step, "launch_ms": launch_ms,
+                         "note": "achieved = algorithmic bytes of the K timed steps / device time of the timed region",
+                         "single_chain": None if serial is None else
+                         {"ms_per_step": serial, "frac": bytes_per_step * B / (serial * 1e-3) / 1e9 / peak,
+                          "note": "same steps as one dependent chain (every launch waits for its predecessor)"}},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": work.h2d,
                     "d2h_bytes_per_step": work.d2h, "steps": Ke},
             "gpu_launches": K * wl["launches"] * world,
@@ -472,6 +511,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stats", action="store_true", help="exploration: skip the fused episode statistics")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (exploration only)")
+    ap.add_argument("--streams", type=int, default=4, help="parallel chains of independent replicas inside the timed graph")
     ap.add_argument("--e2e-depth", type=int, default=0, help="environment batches in flight in the e2e leg (0 = default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
