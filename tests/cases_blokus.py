@@ -235,3 +235,39 @@ def case_random_boards(be, n=96, seed=11):
         assert m2[i, 0] == nst[1] and m2[i, 1] == nxt and bool(m2[i, 2]) == term
         assert r["reward"][i] == rew and r["terminal"][i] == term and r["winners"][i] == (win if term else 0), i
         assert not r["error"][i]
+
+
+def case_many_anchors(be):
+    """Lattice positions with far more anchors than random play ever has (up to ~170: several 16-anchor chunks of
+    the emission, anchors on every row / column, pieces hanging over all four edges): every seat's full ordered
+    list vs the oracle, with short and full inventories."""
+    boards, invs = [], []
+    for step, off, colour in ((3, 1, 1), (3, 0, 2), (4, 1, 3), (3, 2, 4), (5, 2, 1), (2, 0, 2)):
+        b = np.zeros((20, 20), np.int8)
+        b[off::step, off::step] = colour
+        if step == 2:                                   # checkerboard of the even lattice: anchors on all (odd, odd) cells
+            b[:] = 0
+            ys, xs = np.mgrid[0:20:2, 0:20:2]
+            sel = ((ys + xs) % 4 == 0)
+            b[ys[sel], xs[sel]] = colour
+        boards.append(b)
+        invs.append(np.ones((4, 21), np.uint8))
+        boards.append(b.copy())
+        short = np.zeros((4, 21), np.uint8)
+        short[:, [0, 3, 8, 9, 14, 19, 20]] = 1
+        invs.append(short)
+    boards, invs = np.stack(boards), np.stack(invs)
+    n = len(boards)
+    scores = np.zeros((n, 4), np.int64)
+    rounds = np.full(n, 3)
+    movers = np.zeros(n, np.int64)
+    st = blk_pack(be, boards, invs, scores, rounds, movers)
+    most = 0
+    for p in range(4):
+        counts, ids = blk_legal(be, st, player=p, cap=16384)
+        for i in range(n):
+            most = max(most, len(orc.blokus_anchors(boards[i].astype(np.int64), 3, p + 1)))
+            exp = orc.blokus_valid_moves((boards[i].astype(np.int64), 3, invs[i], scores[i]), p, cap=65536)
+            assert counts[i] == len(exp), (i, p, counts[i], len(exp))
+            assert (ids[i, :min(len(exp), 16384)] == exp[:16384]).all(), (i, p)
+    assert most > 128, most

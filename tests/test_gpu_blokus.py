@@ -35,3 +35,7 @@ def test_rollout_vs_oracle_wide(be):
 
 def test_random_boards(be):
     cases.case_random_boards(be, n=160)
+
+
+def test_many_anchors(be):
+    cases.case_many_anchors(be)

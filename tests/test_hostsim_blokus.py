@@ -28,3 +28,7 @@ def test_rollout_vs_oracle(be):
 
 def test_random_boards(be):
     cases.case_random_boards(be, n=20)
+
+
+def test_many_anchors(be):
+    cases.case_many_anchors(be)
