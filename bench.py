@@ -180,7 +180,7 @@ def _pipelined_e2e_step(work, k, probe_col):
     torch = work.torch
     if work.steppers is None:
         work.e2e_streams = [torch.cuda.Stream(work.envs[0].device) for _ in range(E2E_DEPTH)]
-        work.steppers = [e.host_stepper(s, stream=work.e2e_streams[i % E2E_DEPTH])
+        work.steppers = [e.host_stepper(s, stream=work.e2e_streams[i % E2E_DEPTH], **getattr(work, "stepper_kwargs", {}))
                          for i, (e, s) in enumerate(zip(work.envs, work.states))]
         for sp in work.steppers:
             sp()                    # the first replay of a graph uploads it: keep that out of the timing
@@ -216,7 +216,8 @@ class TronWL:
         self.actions = torch.empty((K, B, 4), dtype=torch.int8, device=dev)   # resident inputs of the timed steps
         self.h_actions = [torch.from_numpy(np.random.RandomState(rank + i).randint(-1, 2, size=(B, 4)).astype(np.int8)).pin_memory()
                           for i in range(2)]
-        self.h2d, self.d2h = B * 4, B * 8
+        self.h2d, self.d2h = B * 4, B * 4
+        self.stepper_kwargs = {"compact": True}      # 4-byte result record (terminal | alive | winners | ranking)
         self.steppers = None
 
     def prepare(self, k0, K):
@@ -238,7 +239,7 @@ class TronWL:
         env.step_(st, act, out=st)                             # in place; C-ABI crl_tron_step
 
     def e2e_step(self, k):
-        return _pipelined_e2e_step(self, k, 4)
+        return _pipelined_e2e_step(self, k, 0)
 
     def e2e_drain(self):
         _pipelined_e2e_drain(self)

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcolosseum_b200.so")
 NSTAT = 32
 STAT_ROWS = 256
 FLAG_AUTO_RESET = 1
+FLAG_COMPACT_RESULT = 2      # crl_tron_step: 4-byte result record
 
 _vp, _i64, _i32, _u64, _u32, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, C.c_int
 

@@ -42,20 +42,24 @@ class HostStepper:
     8-byte writes), so the copies stay explicit and the three operations are fused into one graph launch instead.
     """
 
-    def __init__(self, env, state, action_shape, action_dtype, stream=None):
+    def __init__(self, env, state, action_shape, action_dtype, stream=None, step=None):
+        """step(dev_actions) -> device tensor holding the step's result record; default: env.step_ in place on
+        `state`, the full record.  (Tron passes a compact-record step: half the bytes to read back.)"""
         self.env, self.state, self.stream = env, state, stream
         self.actions = torch.zeros(action_shape, dtype=action_dtype).pin_memory()
         self._dev_actions = torch.zeros(action_shape, dtype=action_dtype, device=env.device)
-        env.step_(state, self._dev_actions, out=state)          # allocates state.result; warms the launch path
-        self.result = torch.empty(state.result.shape, dtype=torch.uint8).pin_memory()
+        if step is None:
+            def step(dev_actions):
+                return env.step_(state, dev_actions, out=state).result
+        dev_result = step(self._dev_actions)                    # allocates the record; warms the launch path
+        self.result = torch.empty(dev_result.shape, dtype=torch.uint8).pin_memory()
         self.result_np = self.result.numpy()                    # zero-copy numpy view of the pinned record (cheap reads)
         self.actions_np = self.actions.numpy()
         torch.cuda.synchronize(env.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._dev_actions.copy_(self.actions, non_blocking=True)
-            env.step_(state, self._dev_actions, out=state)
-            self.result.copy_(state.result, non_blocking=True)
+            self.result.copy_(step(self._dev_actions), non_blocking=True)
 
         # replay / completion through the CUDA runtime directly: three ctypes calls per step instead of torch's
         # stream context + event objects (the host loop is CPU-bound)

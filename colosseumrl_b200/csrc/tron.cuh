@@ -406,7 +406,9 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
     if (work) {
         if (!(flags & 0x400)) tron_phase3(c, prm, o);
         tile.v[12][t] = tron_ctx_header(c);
-        result[e0 + t] = tron_pack_result(o);
+        const uint2 rec = tron_pack_result(o);
+        if (flags & CRL_FLAG_COMPACT_RESULT) ((uint32_t *)result)[e0 + t] = rec.y;   // 4-byte record (see the header)
+        else result[e0 + t] = rec;
     }
     tron_tile_store(tile, &maps, out, B, e0, n, false, true);
     // statistics: every warp adds its 17 sums straight to the CTA's row of the global buffer (fire-and-forget RED);

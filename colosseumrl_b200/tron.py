@@ -101,11 +101,36 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
                                             self.num_players, self.flags, self._stream))
         return new
 
-    def host_stepper(self, state: TronBatchState, stream=None):
+    def host_stepper(self, state: TronBatchState, stream=None, compact: bool = False):
         """Graph-fused H2D actions -> step -> D2H result for host-side policies (see base.HostStepper).
+        compact=True: the step writes the 4-byte record (CRL_FLAG_COMPACT_RESULT: terminal | alive | winners | ranking),
+        which halves the PCIe read-back; `decode_compact` rebuilds the reference's return values from it on the host.
         NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
         from .base import HostStepper
-        return HostStepper(self, state, (self.batch, 4), torch.int8, stream=stream)
+        if not compact:
+            return HostStepper(self, state, (self.batch, 4), torch.int8, stream=stream)
+        rec = torch.empty((self.batch, 4), dtype=torch.uint8, device=self.device)
+
+        def step(dev_actions):
+            self._check(self._lib.crl_tron_step(state.packed.data_ptr(), state.packed.data_ptr(), dev_actions.data_ptr(),
+                                                rec.data_ptr(), self._stats_ptr, self.batch, self.N, self.num_players,
+                                                self.flags | _lib.FLAG_COMPACT_RESULT, self._stream))
+            state.result = None                 # the full record of an earlier step no longer describes `state`
+            return rec
+        return HostStepper(self, state, (self.batch, 4), torch.int8, stream=stream, step=step)
+
+    def decode_compact(self, rec):
+        """The reference's next_state return values from compact records (numpy uint8 [B, 4], e.g. HostStepper.wait()):
+        (new_players mask [B], rewards int8 [B, P], terminal [B], winners mask [B], ranking [B, P]).
+        rewards = -2 * (deaths > 0) + 1, winners of a terminal step + 9 (TronGridEnvironment.py:313-320)."""
+        import numpy as np
+        rec = np.asarray(rec)
+        terminal, alive, winners, rk = rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3]
+        p = np.arange(self.num_players, dtype=np.uint8)[None, :]
+        a = (alive[:, None] >> p) & 1
+        w = ((winners[:, None] >> p) & 1) * (terminal[:, None] & 1)
+        rewards = (2 * a.astype(np.int8) - 1 + 9 * w.astype(np.int8)).astype(np.int8)
+        return alive, rewards, terminal, winners, ((rk[:, None] >> (2 * p)) & 3).astype(np.uint8)
 
     def valid_actions(self, state, player):
         """Always ['forward', 'right', 'left'] (:325-341): uint8 [B, 3] of ones."""

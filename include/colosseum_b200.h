@@ -34,6 +34,7 @@ extern "C" {
 #define CRL_PLAYER_ALL (-3)      /* observe (Tron): the views of all players at once */
 
 #define CRL_FLAG_AUTO_RESET 1 /* an environment whose stored terminal flag is set is replaced by new_state() before the step */
+#define CRL_FLAG_COMPACT_RESULT 2 /* crl_tron_step only: write the 4-byte record (below) instead of the 8-byte one */
 
 /* statistics buffer: int64[CRL_STAT_ROWS][CRL_NSTAT] on the device, accumulated (+=) by step / rollout kernels.
  * CTAs spread their partial sums over the rows so that same-address L2 atomics do not serialise; the value of
@@ -69,7 +70,11 @@ int crl_philox_words(uint32_t *out, uint64_t seed, uint64_t first_env, uint32_t 
  * actions: int8[B][4]  (0 forward, +1 right, -1 left; TronGridEnvironment.STRING_TO_ACTION :62-67),
  *          entries of dead / absent players are ignored.
  * result:  8 bytes per environment: int8 reward[4] | u8 terminal | u8 alive mask | u8 winners mask |
- *          u8 ranking (2 bits per player, competition ranking of compute_ranking).              */
+ *          u8 ranking (2 bits per player, competition ranking of compute_ranking).
+ *          With CRL_FLAG_COMPACT_RESULT: 4 bytes per environment = the second half of that record (terminal | alive |
+ *          winners | ranking).  The rewards follow from it exactly as the reference computes them
+ *          (TronGridEnvironment.py:313-320): reward[p] = alive[p] ? 1 : -1, plus 9 for the winners of a terminal step.
+ *          It halves what a host-side actor has to read back over PCIe per step.                  */
 int64_t crl_tron_state_bytes(int N, int P, int64_t B);
 /* HOST function. generate_start_positions (TronGridEnvironment.py:183-226) with new_state's defaults:
  * heads[p] = y*N + x, directions[p] in {0 N, 1 E, 2 S, 3 W}. */

@@ -211,3 +211,31 @@ def case_errors(be):
     assert b"player count" in be.lib.crl_last_error()
     assert be.lib.crl_tron_reset(None, None, 4, 19, 4, be.stream) == 1
     assert be.lib.crl_tron_reset(be.ptr(st), None, 0, 19, 4, be.stream) == 0      # empty batch is fine
+
+
+def case_compact_result(be, N=19, P=4, B=300, K=40, seed=9):
+    """CRL_FLAG_COMPACT_RESULT: the 4-byte record is the second half of the full one, the states are identical, and
+    the reference's rewards (TronGridEnvironment.py:313-320) follow from it: alive ? 1 : -1, +9 for the winners of a
+    terminal step."""
+    rng = np.random.RandomState(seed)
+    full = be.zeros((13, B, 4), np.int32)
+    be.check(be.lib.crl_tron_reset(be.ptr(full), None, B, N, P, be.stream))
+    comp = be.zeros((13, B, 4), np.int32)
+    be.check(be.lib.crl_tron_reset(be.ptr(comp), None, B, N, P, be.stream))
+    seen_terminal = 0
+    for t in range(K):
+        act = rng.randint(-1, 2, size=(B, 4)).astype(np.int8)
+        a = be.upload(act)
+        r8, r4 = be.zeros((B, 8), np.uint8), be.zeros((B, 4), np.uint8)
+        be.check(be.lib.crl_tron_step(be.ptr(full), be.ptr(full), be.ptr(a), be.ptr(r8), None, B, N, P, 1, be.stream))
+        be.check(be.lib.crl_tron_step(be.ptr(comp), be.ptr(comp), be.ptr(a), be.ptr(r4), None, B, N, P, 1 | 2, be.stream))
+        r8, r4 = be.download(r8), be.download(r4)
+        assert (r8[:, 4:] == r4).all(), t
+        assert (be.download(full) == be.download(comp)).all(), t
+        p = np.arange(P)[None, :]
+        alive = (r4[:, 1][:, None] >> p) & 1
+        win = ((r4[:, 2][:, None] >> p) & 1) * (r4[:, 0][:, None] & 1)
+        rewards = 2 * alive.astype(np.int64) - 1 + 9 * win
+        assert (rewards == r8[:, :P].view(np.int8)).all(), t
+        seen_terminal += int(r4[:, 0].sum())
+    assert seen_terminal > 0

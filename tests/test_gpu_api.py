@@ -144,3 +144,29 @@ def test_host_stepper_matches_next_state():
         assert (r2 == sr.result.cpu().numpy()).all() and r1.shape == r2.shape
     torch.cuda.synchronize()
     assert (sc.packed == sr.packed).all()
+
+
+def test_compact_host_stepper():
+    """host_stepper(compact=True): 4-byte records whose decode equals next_state's return values."""
+    from colosseumrl_b200.tron import BatchedTronGridEnvironment
+    B = 513
+    a_env = BatchedTronGridEnvironment("", batch=B, seed=4, auto_reset=True)
+    b_env = BatchedTronGridEnvironment("", batch=B, seed=4, auto_reset=True)
+    sa, _ = a_env.new_state()
+    sb, _ = b_env.new_state()
+    stepper = b_env.host_stepper(sb, compact=True)         # warm-up applies one all-forward step
+    sa, *_ = a_env.next_state(sa, None, torch.zeros((B, 4), dtype=torch.int8))
+    rng = np.random.RandomState(1)
+    terminals = 0
+    for t in range(40):
+        a = rng.randint(-1, 2, size=(B, 4)).astype(np.int8)
+        sa, pa, ra, ta, wa = a_env.next_state(sa, None, torch.from_numpy(a))
+        stepper.actions_np[...] = a
+        rec = stepper()
+        assert rec.shape == (B, 4)
+        alive, rewards, terminal, winners, ranking = b_env.decode_compact(rec)
+        assert (alive == pa.cpu().numpy()).all() and (rewards == ra.cpu().numpy()).all()
+        assert (terminal == ta.cpu().numpy()).all() and (winners == wa.cpu().numpy()).all()
+        assert (ranking == a_env.compute_ranking(sa).cpu().numpy()).all()
+        terminals += int(terminal.sum())
+    assert terminals > 0 and (sa.packed == sb.packed).all()

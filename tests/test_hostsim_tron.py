@@ -39,3 +39,7 @@ def test_in_place_and_masked_reset(be):
 
 def test_errors(be):
     cases.case_errors(be)
+
+
+def test_compact_result(be):
+    cases.case_compact_result(be)
