@@ -165,7 +165,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": "%d envs x %d steps" % (B, args.steps)},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=REAL_STDOUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- GPU workloads
@@ -346,8 +346,6 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     B, K, W = (args.batch or wl["B"]), args.steps, args.warmup
@@ -498,12 +496,26 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.workload)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+REAL_STDOUT = sys.stdout
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on the real stdout and point file descriptor 1 at
+    stderr, so that whatever a library prints (NCCL's version banner, NCCL_DEBUG output, torchrun notices) cannot
+    precede or follow the line."""
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
