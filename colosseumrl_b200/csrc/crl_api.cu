@@ -382,6 +382,16 @@ int crl_ttt_reset(void *state, const uint8_t *mask, int64_t B, int n, crl_stream
     return check_launch("ttt_reset_kernel");
 }
 
+// TTT step / rollout grids: 256 threads, a thread steps up to TTT_ACC_MAX environments (grid-stride) so that the
+// fused statistics are reduced once per thread block pass; small batches keep one environment per thread.
+static unsigned ttt_blocks(int64_t B) {
+    const int64_t one_wave = 148 * 8 * 256;              // B200: 148 SMs x 2048 resident threads
+    int64_t per_thread = (B + one_wave - 1) / one_wave;
+    if (per_thread < 1) per_thread = 1;
+    if (per_thread > TTT_ACC_MAX) per_thread = TTT_ACC_MAX;
+    return blocks_for(B, 256 * per_thread);
+}
+
 int crl_ttt_step(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, uint32_t *valid_after,
                  int64_t *stats, int64_t B, int n, int flags, crl_stream_t stream) {
     TTTParams prm;
@@ -389,7 +399,7 @@ int crl_ttt_step(const void *state_in, void *state_out, const int8_t *actions, u
     if (rc) return rc;
     if (!state_in || !state_out || !actions || !result || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_step: bad argument%s");
     if (B == 0) return CRL_OK;
-#define TTT_STEP(NP) CRL_LAUNCH(ttt_step_kernel<NP>, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state_in, \
+#define TTT_STEP(NP) CRL_LAUNCH(ttt_step_kernel<NP>, ttt_blocks(B), 256, (cudaStream_t)stream, (const uint4 *)state_in, \
                                (uint4 *)state_out, actions, (uint32_t *)result, valid_after, (crl_u64 *)stats, (long long)B, flags)
     if (n == 2) TTT_STEP(2); else if (n == 3) TTT_STEP(3); else TTT_STEP(4);
 #undef TTT_STEP
@@ -427,7 +437,7 @@ int crl_ttt_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed,
     if (rc) return rc;
     if (!state || B < 0 || K < 0) return fail(CRL_ERR_ARG, "crl_ttt_rollout: bad argument%s");
     if (B == 0 || K == 0) return CRL_OK;
-#define TTT_ROLL(NP) CRL_LAUNCH(ttt_rollout_kernel<NP>, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint4 *)state, \
+#define TTT_ROLL(NP) CRL_LAUNCH(ttt_rollout_kernel<NP>, ttt_blocks(B), 256, (cudaStream_t)stream, (uint4 *)state, \
                                (uint32_t *)result, (crl_u64 *)stats, (long long)B, (crl_u64)seed, (crl_u64)first_env, step0, K)
     if (n == 2) TTT_ROLL(2); else if (n == 3) TTT_ROLL(3); else TTT_ROLL(4);
 #undef TTT_ROLL

@@ -105,69 +105,85 @@ __device__ __forceinline__ uint32_t ttt_pack_result(const TTTOut &o) {
            (uint32_t)o.winners << 16 | rank << 24;
 }
 
-// Episode statistics of one step: 15 counters packed into 4 words -> 4 redux.sync per warp; lane l < 15 then extracts
-// counter l from the (warp-uniform) sums and adds it to the CTA's shared partial -- ONE atomic instruction per warp.
-//   lane constants: word (0..3) | shift << 4 | bits << 10 | slot << 16
-#define TTT_SL(word, shift, bits, slot) ((word) | (shift) << 4 | (bits) << 10 | (slot) << 16)
+// Episode statistics: every thread ACCUMULATES the packed counters of up to TTT_ACC_MAX env-steps in four registers
+// (a handful of instructions per env-step), then the warp reduces them once (4 redux.sync), lane l < 15 extracts
+// counter l from the warp-uniform sums and adds it to the CTA's shared partial -- ONE atomic instruction per warp and
+// flush -- and the CTA adds its partial to its row of the global buffer once.  (The first version reduced and
+// flushed after every env-step with two barriers: 40 % of the step kernel's time.)
+//   A: steps | episodes << 8 | episodes without winner << 16 | illegal actions << 24       (sums <= 32 * 4 = 128)
+//   W: wins per seat, 8 bits each.    The "not a winner" counters follow: rank[q] = episodes - wins[q]
+//   D: valid-action count (12 bits: <= 27 * 128) | episode length of finished episodes << 12 (<= 31 * 128)
+//   R: (mover + 1) * reward, biased by +4 per env-step (<= 8 * 128)
+//   lane constants: word (0..3) | shift << 4 | bits << 10 | slot << 16 | kind << 24 (1: episodes - x, 2: x - 4 * steps)
+#define TTT_ACC_MAX 4
+#define TTT_SL(word, shift, bits, slot, kind) ((word) | (shift) << 4 | (bits) << 10 | (slot) << 16 | (kind) << 24)
 __constant__ uint32_t TTT_STAT_LANE[32] = {
-    TTT_SL(0, 0, 8, ST_STEPS), TTT_SL(0, 8, 8, ST_EPISODES), TTT_SL(0, 16, 8, ST_NOWIN), TTT_SL(0, 24, 8, ST_ERRORS),
-    TTT_SL(1, 0, 8, ST_WINS + 0), TTT_SL(1, 8, 8, ST_WINS + 1), TTT_SL(1, 16, 8, ST_WINS + 2), TTT_SL(1, 24, 8, ST_WINS + 3),
-    TTT_SL(2, 0, 8, ST_RANK + 0), TTT_SL(2, 8, 8, ST_RANK + 1), TTT_SL(2, 16, 8, ST_RANK + 2), TTT_SL(2, 24, 8, ST_RANK + 3),
-    TTT_SL(3, 0, 10, ST_NVALID), TTT_SL(3, 10, 10, ST_EPLEN), TTT_SL(3, 20, 12, ST_REWARD),
+    TTT_SL(0, 0, 8, ST_STEPS, 0), TTT_SL(0, 8, 8, ST_EPISODES, 0), TTT_SL(0, 16, 8, ST_NOWIN, 0), TTT_SL(0, 24, 8, ST_ERRORS, 0),
+    TTT_SL(1, 0, 8, ST_WINS + 0, 0), TTT_SL(1, 8, 8, ST_WINS + 1, 0), TTT_SL(1, 16, 8, ST_WINS + 2, 0), TTT_SL(1, 24, 8, ST_WINS + 3, 0),
+    TTT_SL(1, 0, 8, ST_RANK + 0, 1), TTT_SL(1, 8, 8, ST_RANK + 1, 1), TTT_SL(1, 16, 8, ST_RANK + 2, 1), TTT_SL(1, 24, 8, ST_RANK + 3, 1),
+    TTT_SL(2, 0, 12, ST_NVALID, 0), TTT_SL(2, 12, 12, ST_EPLEN, 0), TTT_SL(3, 0, 12, ST_REWARD, 2),
     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define TTT_STAT_LANES 15
 
-template <int NP>
-__device__ __forceinline__ void ttt_stats(int *sm_stat, bool valid, const TTTOut &o, int mover, uint32_t ep_len, uint32_t lane_const) {
-    const uint32_t t = (valid && o.terminal) ? 1u : 0u;
-    const uint32_t w = t ? (uint32_t)o.winners : 0u, r = t ? (((1u << NP) - 1u) & ~(uint32_t)o.winners) : 0u;
-    // fields hold sums over <= 32 lanes: 8-bit fields for 0/1 values, wider ones where needed
-    uint32_t A = (valid ? 1u : 0u) | t << 8 | (t & (o.winners == 0)) << 16 | (valid ? (uint32_t)o.error : 0u) << 24;
-    uint32_t Bw = (w & 1u) | (w >> 1 & 1u) << 8 | (w >> 2 & 1u) << 16 | (w >> 3 & 1u) << 24;
-    uint32_t C = (r & 1u) | (r >> 1 & 1u) << 8 | (r >> 2 & 1u) << 16 | (r >> 3 & 1u) << 24;
-    uint32_t D = (valid ? (uint32_t)o.nvalid : 0u) | (t ? min(ep_len, 31u) : 0u) << 10 |
-                 (uint32_t)((valid ? (mover + 1) * o.reward : 0) + 4) << 20;           // reward biased by +4 per lane
-    A = __reduce_add_sync(0xffffffffu, A); Bw = __reduce_add_sync(0xffffffffu, Bw);
-    C = __reduce_add_sync(0xffffffffu, C); D = __reduce_add_sync(0xffffffffu, D);
-    const uint32_t word = lane_const & 15u;
-    const uint32_t x = (A & -(uint32_t)(word == 0u)) | (Bw & -(uint32_t)(word == 1u)) | (C & -(uint32_t)(word == 2u)) |
-                       (D & -(uint32_t)(word == 3u));
-    int val = (int)((x >> ((lane_const >> 4) & 31u)) & ((1u << ((lane_const >> 10) & 31u)) - 1u));
-    const int slot = (int)(lane_const >> 16);
-    if (slot == ST_REWARD) val -= 4 * 32;
-    if ((int)(threadIdx.x & 31) < TTT_STAT_LANES && val != 0) atomicAdd(&sm_stat[slot], val);
-}
+struct TTTStatAcc {
+    uint32_t A, W, D, R;
+    __device__ __forceinline__ void clear() { A = W = D = R = 0u; }
+    // one env-step of a live thread
+    template <int NP>
+    __device__ __forceinline__ void add(const TTTOut &o, int mover, uint32_t ep_len) {
+        const uint32_t t = o.terminal ? 1u : 0u;
+        const uint32_t w = t ? (uint32_t)o.winners : 0u;
+        A += 1u | t << 8 | (t & (uint32_t)(o.winners == 0)) << 16 | (uint32_t)o.error << 24;
+        W += (w * 0x00204081u) & 0x01010101u;                               // bit q -> byte q
+        D += (uint32_t)o.nvalid | (t ? min(ep_len, 31u) : 0u) << 12;
+        R += (uint32_t)((mover + 1) * o.reward + 4);
+    }
+    // warp-collective: reduce, extract, add to the CTA's shared partial, clear
+    template <int NP>
+    __device__ __forceinline__ void flush(int *sm_stat, uint32_t lane_const) {
+        const uint32_t a = __reduce_add_sync(0xffffffffu, A), w = __reduce_add_sync(0xffffffffu, W);
+        const uint32_t d = __reduce_add_sync(0xffffffffu, D), r = __reduce_add_sync(0xffffffffu, R);
+        const uint32_t word = lane_const & 15u;
+        const uint32_t x = word == 0u ? a : word == 1u ? w : word == 2u ? d : r;
+        int val = (int)((x >> ((lane_const >> 4) & 31u)) & ((1u << ((lane_const >> 10) & 31u)) - 1u));
+        const uint32_t kind = lane_const >> 24;
+        if (kind == 1u) val = ((lane_const >> 7) & 7u) < (uint32_t)NP ? (int)((a >> 8) & 255u) - val : 0;   // not-a-winner, seats < NP
+        if (kind == 2u) val -= 4 * (int)(a & 255u);                         // remove the reward bias
+        const int slot = (int)((lane_const >> 16) & 255u);
+        if ((int)(threadIdx.x & 31) < TTT_STAT_LANES && val != 0) atomicAdd(&sm_stat[slot], val);
+        clear();
+    }
+};
 
 __device__ __forceinline__ void ttt_zero_out(TTTOut &o) {
     o.reward = o.terminal = o.error = o.placed = o.winners = o.nvalid = 0; o.valid_after = 0;
 }
 
+// Grid-stride: the launcher sizes the grid so that a thread steps at most TTT_ACC_MAX environments.
 template <int NP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int8_t *__restrict__ actions,
                 uint32_t *__restrict__ result, uint32_t *__restrict__ valid_after, crl_u64 *stats, long long B,
                 int flags) {
     __shared__ int sm_stat[CRL_NSTAT];
     if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = e < B;
-    TTTOut o;
-    ttt_zero_out(o);
-    int mover = 0;
-    uint32_t ep_len = 0;
-    if (valid) {
+    TTTStatAcc acc;
+    acc.clear();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < B; e += stride) {
         TTTEnv s;
+        TTTOut o;
         ttt_decode(s, ld_stream(in + e));
         if ((flags & CRL_FLAG_AUTO_RESET) && ttt_is_terminal<NP>(s)) ttt_new_state(s);
-        mover = s.mover;
+        const int mover = s.mover;
         ttt_step_env<NP>(s, (int)actions[e], o);
-        ep_len = s.ep_len;
         st_stream(out + e, ttt_encode(s));
         result[e] = ttt_pack_result<NP>(o);
         if (valid_after) valid_after[e] = o.valid_after;
+        if (stats) acc.add<NP>(o, mover, s.ep_len);
     }
     if (stats) {
-        ttt_stats<NP>(sm_stat, valid, o, mover, ep_len, TTT_STAT_LANE[threadIdx.x & 31]);
+        acc.flush<NP>(sm_stat, TTT_STAT_LANE[threadIdx.x & 31]);
         __syncthreads();
         stats_flush_row(sm_stat, stats);
     }
@@ -207,35 +223,44 @@ __global__ void ttt_policy_random_kernel(const uint4 *__restrict__ st, int8_t *_
     actions[e] = (int8_t)ttt_random_action<NP>(s, r.x);
 }
 
+// K fused random-policy steps with auto-reset; grid-stride like the step kernel (a thread owns <= TTT_ACC_MAX
+// environments and keeps one of them in registers for the K steps).
 template <int NP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl_u64 *stats, long long B,
                    crl_u64 seed, crl_u64 first_env, uint32_t step0, int K) {
     __shared__ int sm_stat[CRL_NSTAT];
     if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = e < B;
-    TTTEnv s;
-    TTTOut o;
-    ttt_zero_out(o);
-    ttt_new_state(s);
-    if (valid) ttt_decode(s, ld_stream(state + e));
     const uint32_t lane_const = TTT_STAT_LANE[threadIdx.x & 31];
-    for (int k = 0; k < K; k++) {
-        int mover = 0;
-        if (valid) {
-            if (ttt_is_terminal<NP>(s)) ttt_new_state(s);
-            uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TTT);
-            mover = s.mover;
-            ttt_step_env<NP>(s, ttt_random_action<NP>(s, r.x), o);
+    TTTStatAcc acc;
+    acc.clear();
+    int pending = 0;                                     // env-steps accumulated since the last flush (block-uniform)
+    const long long stride = (long long)gridDim.x * blockDim.x, first = (long long)blockIdx.x * blockDim.x;
+    for (long long e0 = first; e0 < B; e0 += stride) {   // block-uniform trip count: the flushes are warp-collective
+        const long long e = e0 + threadIdx.x;
+        const bool valid = e < B;
+        TTTEnv s;
+        TTTOut o;
+        ttt_zero_out(o);
+        ttt_new_state(s);
+        if (valid) ttt_decode(s, ld_stream(state + e));
+        for (int k = 0; k < K; k++) {
+            if (valid) {
+                if (ttt_is_terminal<NP>(s)) ttt_new_state(s);
+                const uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TTT);
+                const int mover = s.mover;
+                ttt_step_env<NP>(s, ttt_random_action<NP>(s, r.x), o);
+                if (stats) acc.add<NP>(o, mover, s.ep_len);
+            }
+            if (stats && ++pending == TTT_ACC_MAX) { acc.flush<NP>(sm_stat, lane_const); pending = 0; }
         }
-        if (stats) ttt_stats<NP>(sm_stat, valid, o, mover, s.ep_len, lane_const);
-    }
-    if (valid) {
-        st_stream(state + e, ttt_encode(s));
-        if (result) result[e] = ttt_pack_result<NP>(o);
+        if (valid) {
+            st_stream(state + e, ttt_encode(s));
+            if (result) result[e] = ttt_pack_result<NP>(o);
+        }
     }
     if (stats) {
+        if (pending) acc.flush<NP>(sm_stat, lane_const);
         __syncthreads();
         stats_flush_row(sm_stat, stats);
     }

@@ -38,7 +38,11 @@ def timed(name, fn, bytes_per_env, chains):
           (name, chains, us, B / us / 1e3, bytes_per_env * B / us / 1e3, bytes_per_env * B / us / 1e3 / PEAK))
 
 
-for ch in (1, 4):
-    timed("next_state (crl_ttt_step, resident actions)", lambda g, k: envs[g].step_(states[g], acts[g], out=states[g]), 41, ch)
-    timed("random policy (crl_ttt_policy_random)", lambda g, k: envs[g].random_actions(states[g], k, out=acts[g]), 17, ch)
-    timed("fused policy + step (crl_ttt_rollout, K=1)", lambda g, k: envs[g].rollout(states[g], k, 1), 36, ch)
+for stats in (True, False):
+  for e in envs:
+      e.collect_stats = stats
+  print("statistics", "on" if stats else "off")
+  for ch in (1, 4):
+      timed("next_state (crl_ttt_step, resident actions)", lambda g, k: envs[g].step_(states[g], acts[g], out=states[g]), 41, ch)
+      timed("random policy (crl_ttt_policy_random)", lambda g, k: envs[g].random_actions(states[g], k, out=acts[g]), 17, ch)
+      timed("fused policy + step (crl_ttt_rollout, K=1)", lambda g, k: envs[g].rollout(states[g], k, 1), 36, ch)
