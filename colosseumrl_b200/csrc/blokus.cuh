@@ -297,12 +297,12 @@ __device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int 
                 while (h != 0u && __popc(h) > max(cap - pos, 0)) h &= ~(0x80000000u >> __clz((int)h));
             const uint32_t w = sm.anch[a0 + 4 * g + a];
             const int val0 = (int)(w >> 9) * 200 + (int)(w & 31u) * 40 + val00;      // (y * 20 + x) * 40 + ...
-            int32_t *q = out + pos;
-            if (h & 1u) st_global_u32(q++, val0);
-            if (h & 2u) st_global_u32(q++, val0 + 1);
-            if (h & 4u) st_global_u32(q++, val0 + 2);
-            if (h & 8u) st_global_u32(q++, val0 + 3);
-            if (h & 16u) st_global_u32(q, val0 + 4);
+            // (32-bit running index: a 64-bit running pointer costs predicated 64-bit adds and moves per store)
+            if (h & 1u) st_global_u32(out + pos++, val0);
+            if (h & 2u) st_global_u32(out + pos++, val0 + 1);
+            if (h & 4u) st_global_u32(out + pos++, val0 + 2);
+            if (h & 8u) st_global_u32(out + pos++, val0 + 3);
+            if (h & 16u) st_global_u32(out + pos, val0 + 4);
         }
     }
 #undef BLK_TEST
