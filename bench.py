@@ -314,22 +314,61 @@ class BlokusWL:
         env.step_(st, self.act[g], out=st)                            # crl_blokus_step
         self.local_t[g] += 1
 
-    def e2e_drain(self):
-        pass
+    # e2e: a host-side policy needs two round trips per step -- it sees the list lengths (D2H), picks an index into
+    # the device-side list (H2D of one int32 per game; here: entry 0, -1 = pass), the step runs, the result record
+    # comes back (D2H).  The actor pipelines its G independent batches, one stream each: while batch g waits for its
+    # counts, batches g-1 .. g-4 are stepping and g-5 .. g-8 are delivering results.
+    E2E_LAG = 4
+
+    def _e2e_init(self):
+        torch = self.torch
+        dev = self.envs[0].device
+        self.es = [torch.cuda.Stream(dev) for _ in range(self.G)]
+        self.ev_a = [torch.cuda.Event() for _ in range(self.G)]
+        self.ev_b = [torch.cuda.Event() for _ in range(self.G)]
+        self.hc = [torch.empty((self.B,), dtype=torch.int32).pin_memory() for _ in range(self.G)]
+        self.hr = [torch.empty((self.B, 8), dtype=torch.uint8).pin_memory() for _ in range(self.G)]
+        self.qa, self.qb = [], []
+        torch.cuda.synchronize(dev)
+
+    def _e2e_phase_b(self, g):
+        torch = self.torch
+        env, st = self.envs[g], self.states[g]
+        self.ev_a[g].synchronize()
+        _ = int(self.hc[g][0])                                        # the host policy reads the list lengths
+        counts, ids = self.valid[g]
+        with torch.cuda.stream(self.es[g]):
+            idx = self.h_actions.to(env.device, non_blocking=True)    # H2D: the host's choice (-1 -> entry 0)
+            act = torch.where(counts > 0, ids[:, 0], idx)
+            new = env.step_(st, act, out=st)
+            self.hr[g].copy_(new.result, non_blocking=True)
+            self.ev_b[g].record()
+        self.qb.append(g)
+
+    def _e2e_phase_c(self, g):
+        self.ev_b[g].synchronize()
+        return int(self.hr[g][0, 1])                                  # the host reads the result record
 
     def e2e_step(self, k):
-        # host-side policy sees the counts (D2H), picks "first legal move" on the device-side list via an index
-        # (H2D of one int32 per game), then steps; the result record comes back (D2H).
+        torch = self.torch
+        if getattr(self, "es", None) is None:
+            self._e2e_init()
         g = k % self.G
-        env, st = self.envs[g], self.states[g]
-        counts, ids = env.valid_actions(st, -1, out=self.valid[g])
-        self.h_counts.copy_(counts, non_blocking=True)
-        self.torch.cuda.current_stream().synchronize()
-        idx = self.h_actions.to(env.device, non_blocking=True)        # H2D: the host's choice (here: -1 -> entry 0)
-        act = self.torch.where(counts > 0, ids[:, 0], idx)
-        new, _, reward, terminal, winners = env.next_state(st, None, act, out=st)
-        self.h_result.copy_(new.result, non_blocking=True)
-        self.torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(self.es[g]):
+            counts, _ = self.envs[g].valid_actions(self.states[g], -1, out=self.valid[g])
+            self.hc[g].copy_(counts, non_blocking=True)
+            self.ev_a[g].record()
+        self.qa.append(g)
+        if len(self.qa) > self.E2E_LAG:
+            self._e2e_phase_b(self.qa.pop(0))
+        if len(self.qb) > self.E2E_LAG:
+            self._e2e_phase_c(self.qb.pop(0))
+
+    def e2e_drain(self):
+        while getattr(self, "qa", None):
+            self._e2e_phase_b(self.qa.pop(0))
+        while getattr(self, "qb", None):
+            self._e2e_phase_c(self.qb.pop(0))
 
     @property
     def stats_env(self):
