@@ -203,24 +203,43 @@ __device__ __forceinline__ int ttt_kth_bit(uint32_t mask, int k) {
     return pos;
 }
 
+// Exact r % n for n <= 27 without the generic 32-bit division (~20 instructions): lane l holds floor(2^32 / l), a
+// shuffle fetches the entry of the lane's own n, q' = umulhi(r, M[n]) is the quotient or one less, one correction.
+// (n = 1: M = 2^32 - 1, q' = r - 1, the correction gives 0.)  Warp-collective: call with all lanes.
+__device__ const uint32_t TTT_RCP_G[32] = {      // floor(2^32 / l); l < 2: 2^32 - 1   (global: one coalesced load per warp)
+    0xffffffffu, 0xffffffffu, 0x80000000u, 0x55555555u, 0x40000000u, 0x33333333u, 0x2aaaaaaau, 0x24924924u,
+    0x20000000u, 0x1c71c71cu, 0x19999999u, 0x1745d174u, 0x15555555u, 0x13b13b13u, 0x12492492u, 0x11111111u,
+    0x10000000u, 0x0f0f0f0fu, 0x0e38e38eu, 0x0d79435eu, 0x0cccccccu, 0x0c30c30cu, 0x0ba2e8bau, 0x0b21642cu,
+    0x0aaaaaaau, 0x0a3d70a3u, 0x09d89d89u, 0x097b425eu, 0x09249249u, 0x08d3dcb0u, 0x08888888u, 0x08421084u};
+__device__ __forceinline__ uint32_t ttt_rcp_lane() { return TTT_RCP_G[threadIdx.x & 31u]; }
+__device__ __forceinline__ uint32_t ttt_mod_small(uint32_t r, uint32_t n, uint32_t rcp_lane) {
+    const uint32_t m = __shfl_sync(0xffffffffu, rcp_lane, (int)n);
+    uint32_t rem = r - __umulhi(r, m) * n;
+    return rem >= n ? rem - n : rem;
+}
+
 // uniform random policy: the (r0 % n_empty)-th empty cell in C order, pass (-1) if the board is full
+// (warp-collective because of ttt_mod_small)
 template <int NP>
-__device__ __forceinline__ int ttt_random_action(const TTTEnv &s, uint32_t r0) {
+__device__ __forceinline__ int ttt_random_action(const TTTEnv &s, uint32_t r0, uint32_t rcp_lane) {
     uint32_t empty = ~(s.m[0] | s.m[1] | s.m[2] | s.m[3]) & TTTGeo<NP>::CELLMASK;
-    int n = __popc(empty);
-    return n ? ttt_kth_bit(empty, (int)(r0 % (uint32_t)n)) : -1;
+    const int n = __popc(empty);
+    const uint32_t k = ttt_mod_small(r0, (uint32_t)max(n, 1), rcp_lane);
+    return n ? ttt_kth_bit(empty, (int)k) : -1;
 }
 
 template <int NP>
 __global__ void ttt_policy_random_kernel(const uint4 *__restrict__ st, int8_t *__restrict__ actions, long long B,
                                          int flags, crl_u64 seed, crl_u64 first_env, uint32_t step) {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B) return;
+    const bool valid = e < B;
     TTTEnv s;
-    ttt_decode(s, st[e]);
+    ttt_new_state(s);
+    if (valid) ttt_decode(s, st[e]);
     if ((flags & CRL_FLAG_AUTO_RESET) && ttt_is_terminal<NP>(s)) ttt_new_state(s);
     uint4 r = env_words(seed, first_env + (crl_u64)e, step, CRL_TAG_TTT);
-    actions[e] = (int8_t)ttt_random_action<NP>(s, r.x);
+    const int a = ttt_random_action<NP>(s, r.x, ttt_rcp_lane());
+    if (valid) actions[e] = (int8_t)a;
 }
 
 // K fused random-policy steps with auto-reset; grid-stride like the step kernel (a thread owns <= TTT_ACC_MAX
@@ -231,7 +250,7 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
                    crl_u64 seed, crl_u64 first_env, uint32_t step0, int K) {
     __shared__ int sm_stat[CRL_NSTAT];
     if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
-    const uint32_t lane_const = TTT_STAT_LANE[threadIdx.x & 31];
+    const uint32_t lane_const = TTT_STAT_LANE[threadIdx.x & 31], rcp_lane = ttt_rcp_lane();
     TTTStatAcc acc;
     acc.clear();
     int pending = 0;                                     // env-steps accumulated since the last flush (block-uniform)
@@ -244,14 +263,12 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
         ttt_zero_out(o);
         ttt_new_state(s);
         if (valid) ttt_decode(s, ld_stream(state + e));
-        for (int k = 0; k < K; k++) {
-            if (valid) {
-                if (ttt_is_terminal<NP>(s)) ttt_new_state(s);
-                const uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TTT);
-                const int mover = s.mover;
-                ttt_step_env<NP>(s, ttt_random_action<NP>(s, r.x), o);
-                if (stats) acc.add<NP>(o, mover, s.ep_len);
-            }
+        for (int k = 0; k < K; k++) {                    // (lanes past the end of the batch step a dummy board)
+            if (ttt_is_terminal<NP>(s)) ttt_new_state(s);
+            const uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TTT);
+            const int mover = s.mover;
+            ttt_step_env<NP>(s, ttt_random_action<NP>(s, r.x, rcp_lane), o);
+            if (stats && valid) acc.add<NP>(o, mover, s.ep_len);
             if (stats && ++pending == TTT_ACC_MAX) { acc.flush<NP>(sm_stat, lane_const); pending = 0; }
         }
         if (valid) {
