@@ -290,12 +290,12 @@ class BlokusWL:
         from colosseumrl_b200.blokus import BatchedBlokusEnvironment
         self.torch, self.B, self.G = torch, B, G
         self.envs = [BatchedBlokusEnvironment("", batch=B, device=dev, seed=0, auto_reset=True,
-                                              first_env_id=(rank * G + g) * B, capacity=2048) for g in range(G)]
+                                              first_env_id=(rank * G + g) * B, capacity=4096) for g in range(G)]
         self.states = [e.new_state()[0] for e in self.envs]
         for e in self.envs[1:]:
             e.stats_rows = self.envs[0].stats_rows
         self.local_t = [0] * G
-        self.valid = [(torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B, 2048), dtype=torch.int32, device=dev))
+        self.valid = [(torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B, 4096), dtype=torch.int32, device=dev))
                       for _ in range(G)]
         self.act = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(G)]
         self.h_actions = torch.full((B,), -1, dtype=torch.int32).pin_memory()
@@ -329,6 +329,16 @@ class BlokusWL:
         self.hc = [torch.empty((self.B,), dtype=torch.int32).pin_memory() for _ in range(self.G)]
         self.hr = [torch.empty((self.B, 8), dtype=torch.uint8).pin_memory() for _ in range(self.G)]
         self.qa, self.qb = [], []
+        torch.cuda.synchronize(dev)
+        # untimed warm-up of EVERY batch's pipeline: the first use of a stream makes the caching allocator cudaMalloc a
+        # pool for it (milliseconds, device-synchronising) -- that belongs to start-up, not to a steady-state step
+        for g in range(self.G):
+            with torch.cuda.stream(self.es[g]):
+                counts, _ = self.envs[g].valid_actions(self.states[g], -1, out=self.valid[g])
+                self.hc[g].copy_(counts, non_blocking=True)
+                self.ev_a[g].record()
+            self._e2e_phase_b(g)
+            self._e2e_phase_c(self.qb.pop(0))
         torch.cuda.synchronize(dev)
 
     def _e2e_phase_b(self, g):
@@ -486,9 +496,15 @@ def run_b200(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    dbg = [] if os.environ.get("CRL_E2E_DEBUG") else None
     for j in range(Ke):
+        t_ = time.perf_counter()
         work.e2e_step(k); k += 1
+        if dbg is not None:
+            dbg.append(time.perf_counter() - t_)
     work.e2e_drain()
+    if dbg:
+        sys.stderr.write("e2e per-call ms: " + " ".join("%.2f" % (x * 1e3) for x in dbg) + "\n")
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)

@@ -67,9 +67,10 @@ class BlokusBatchState:
 
 class BatchedBlokusEnvironment(BatchedBaseEnvironment):
     def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
-                 first_env_id: int = 0, capacity: int = 2048):
+                 first_env_id: int = 0, capacity: int = 4096):
         super().__init__(config, batch, device, seed, auto_reset, first_env_id)
-        self.capacity = int(capacity)      # slots per game in the valid-action list (reference max observed: 1753)
+        self.capacity = int(capacity)      # slots per game in the valid-action list (longest list seen in 16 384 random
+                                           # games x 70 steps: 2 104; counts > capacity signals a truncated list)
 
     @property
     def min_players(self) -> int:

@@ -33,6 +33,12 @@ def test_rollout_vs_oracle_wide(be):
     cases.case_rollout_vs_oracle(be, B=1024, K=150, seed=0, env0=0)
 
 
+def test_rollout_vs_oracle_full_size(be):
+    # BASELINE.json configs[2] at its full size: 16 384 games x 70 steps (one full episode and the restart), end
+    # states and the fused statistics bit-exact vs the oracle (~20 s of oracle time on the box's host cores)
+    cases.case_rollout_vs_oracle(be, B=16384, K=70, seed=2, env0=0, cap=4096)
+
+
 def test_random_boards(be):
     cases.case_random_boards(be, n=160)
 
