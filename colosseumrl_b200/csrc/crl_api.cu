@@ -451,8 +451,10 @@ int crl_ttt_observe(const void *state, int player, int8_t *board, int8_t *winner
     if (rc) return rc;
     if (!state || !board || B < 0 || player >= n || player < -2) return fail(CRL_ERR_ARG, "crl_ttt_observe: bad argument%s");
     if (B == 0) return CRL_OK;
-    CRL_LAUNCH(ttt_observe_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state,
-               (long long)B, prm, player, board, winner, mover);
+#define TTT_OBS(NP) CRL_LAUNCH(ttt_observe_kernel<NP>, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint4 *)state, \
+                              (long long)B, player, board, winner, mover)
+    if (n == 2) TTT_OBS(2); else if (n == 3) TTT_OBS(3); else TTT_OBS(4);
+#undef TTT_OBS
     return check_launch("ttt_observe_kernel");
 }
 

@@ -297,15 +297,22 @@ __global__ void ttt_valid_kernel(const uint4 *__restrict__ st, uint32_t *__restr
     mask[e] = ~(v.x | v.y | v.z | v.w) & prm.cellmask;
 }
 
-// state_to_observation (2p :382-407).  A warp unpacks 32 environments: their `cells` * 32 output bytes are contiguous, so
-// in pass k lane l produces byte 32 k + l (environment (32 k + l) / cells of the warp, fetched with shuffles) and every
-// store instruction writes 32 consecutive bytes.  player == -1: absolute; -2: each game seen by its current mover
-// (CRL_PLAYER_MOVER).  mod = 2 (2p) or 3 (3p AND 4p, tictactoe_4p_env.py:50).
+// state_to_observation (2p :382-407).  A warp unpacks 32 environments.  Lane = environment: the viewer-relative label
+// of every player's cells (absolute: p; else (p - viewer) mod 2 for 2p, mod 3 for 3p AND 4p -- tictactoe_4p_env.py:50)
+// is folded into two label bit-planes + the occupancy plane, four cells at a time are spread to bytes with one
+// multiply each ((nibble * 0x00204081) & 0x01010101: bit i -> byte i) and combined into a word of int8 cells
+// (-1 = empty), which goes to the lane's CELLS-byte slot of the warp's staging tile.  The tile (32 * CELLS bytes,
+// contiguous in the output and 16-byte aligned) then leaves with 128-bit stores.
+// player == -1: absolute; -2: each game seen by its current mover (CRL_PLAYER_MOVER).
 // board int8[B][cells] (-1 empty); winner int8[B] (-1 None); mover int8[B].
+template <int NP>
 __global__ void __launch_bounds__(256)
-ttt_observe_kernel(const uint4 *__restrict__ st, long long B, TTTParams prm, int player,
-                   int8_t *__restrict__ board, int8_t *__restrict__ winner, int8_t *__restrict__ mover) {
-    const int lane = threadIdx.x & 31;
+ttt_observe_kernel(const uint4 *__restrict__ st, long long B, int player, int8_t *__restrict__ board,
+                   int8_t *__restrict__ winner, int8_t *__restrict__ mover) {
+    constexpr int CELLS = TTTGeo<NP>::CELLS, GROUPS = (CELLS + 3) / 4, MOD = NP == 2 ? 2 : 3;
+    constexpr int TILE = 32 * CELLS;                         // 288 / 480 / 864: multiples of 16
+    __shared__ __align__(16) uint8_t stage[8][TILE + 16];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll;      // first environment of the warp
     if (e0 >= B) return;
     const long long e = e0 + lane;
@@ -316,23 +323,34 @@ ttt_observe_kernel(const uint4 *__restrict__ st, long long B, TTTParams prm, int
         if (winner) winner[e] = (int8_t)(s.winner1 - 1);
         if (mover) mover[e] = (int8_t)s.mover;
     }
-    const int cells = prm.cells, mod = prm.n == 2 ? 2 : 3;
-    const uint32_t magic = (65536u + (uint32_t)cells - 1u) / (uint32_t)cells;                 // exact b / cells for b < 32 * cells
-    const int nbytes = (int)min(32ll, B - e0) * cells;
-    for (int k = 0; k < cells; k++) {
-        const int b = 32 * k + lane;
-        const int el = (int)(((uint32_t)b * magic) >> 16), c = b - el * cells;
-        const uint32_t m0 = __shfl_sync(0xffffffffu, s.m[0], el), m1 = __shfl_sync(0xffffffffu, s.m[1], el);
-        const uint32_t m2 = __shfl_sync(0xffffffffu, s.m[2], el), m3 = __shfl_sync(0xffffffffu, s.m[3], el);
-        const int viewer = player == -2 ? __shfl_sync(0xffffffffu, s.mover, el) : player;
-        int v = -1;
-        v = (m0 >> c & 1u) ? 0 : v; v = (m1 >> c & 1u) ? 1 : v; v = (m2 >> c & 1u) ? 2 : v; v = (m3 >> c & 1u) ? 3 : v;
-        if (v >= 0 && viewer >= 0) {
-            v -= viewer;                                    // (v - viewer) mod `mod`, result in 0..mod-1
-            v = v % mod;
-            v += v < 0 ? mod : 0;
-        }
-        if (b < nbytes) board[e0 * cells + b] = (int8_t)v;
+    const int viewer = player == -2 ? s.mover : player;
+    uint32_t b0 = 0u, b1 = 0u;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        const int code = viewer < 0 ? p : ((p - viewer) % MOD + MOD) % MOD;
+        b0 |= (code & 1) ? s.m[p] : 0u;
+        b1 |= (code & 2) ? s.m[p] : 0u;
+    }
+    const uint32_t emp = ~(s.m[0] | s.m[1] | s.m[2] | s.m[3]);
+    uint8_t *mine = stage[wid] + lane * CELLS;
+#pragma unroll
+    for (int j = 0; j < GROUPS; j++) {
+        const uint32_t x0 = (((b0 >> (4 * j)) & 15u) * 0x00204081u) & 0x01010101u;
+        const uint32_t x1 = (((b1 >> (4 * j)) & 15u) * 0x00204081u) & 0x01010101u;
+        const uint32_t xe = (((emp >> (4 * j)) & 15u) * 0x00204081u) & 0x01010101u;
+        const uint32_t word = x0 + 2u * x1 + 255u * xe;      // empty cells have no label bits: 0xff = -1
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (4 * j + i < CELLS) mine[4 * j + i] = (uint8_t)(word >> (8 * i));
+    }
+    __syncwarp();
+    int8_t *dst = board + e0 * CELLS;
+    if (B - e0 >= 32) {
+        const uint4 *src4 = (const uint4 *)stage[wid];
+        for (int i = lane; i < TILE / 16; i += 32) ((uint4 *)dst)[i] = src4[i];
+    } else {
+        const int nbytes = (int)(B - e0) * CELLS;
+        for (int i = lane; i < nbytes; i += 32) dst[i] = (int8_t)stage[wid][i];
     }
 }
 
