@@ -514,9 +514,15 @@ __global__ void blokus_reset_kernel(uint4 *__restrict__ st, const uint8_t *__res
     st[idx] = (v == 20) ? make_uint4(full, full, full, full) : make_uint4(0, 0, 0, 0);
 }
 
-// state_to_observation (BlokusEnvironment.py:721-768): one warp per game.  The 352-byte state is loaded with 22
-// coalesced 128-bit accesses into shared memory; lane l then produces output cells l, l + 32, ... so that every
-// store instruction of the warp writes 32 consecutive bytes.
+// state_to_observation (BlokusEnvironment.py:721-768): one warp per game, bit-plane work instead of per-cell work.
+//  1. lanes = source rows: the cell labels (relative id (c - player) & 3, or c + 1 in the absolute view) are folded into
+//     label bit-planes x0, x1, x2 + the empty plane of the row (a handful of LOP3s, the label of a colour is uniform);
+//  2. 4 cells at a time are spread to bytes with one multiply per plane ((nibble * 0x00204081) & 0x01010101: bit i ->
+//     byte i) and combined into a word of int8 cells, 5 words per source row;
+//  3. np.rot90(k=-player) is where the row lands in the staging tile: whole words for the unrotated views, bytes at
+//     base + stride * x for the rotated ones; the game's 400 board bytes then leave with 25 128-bit stores.
+// (The per-cell version -- 13 passes of 32 cells with a division, four plane tests and a byte store each -- executed
+// 840 warp instructions per game.)
 //  player >= 0: board int8[B][20][20] of relative player ids (-1 empty) rotated by np.rot90(k=-player);
 //               pieces u8[B][4][21] rows by relative id; score int32[B][4] rolled by -player.
 //  player == -1: absolute unpack: board = Board.board_contents (0 empty, 1..4 colour), pieces / score in seat order.
@@ -526,6 +532,7 @@ __global__ void __launch_bounds__(32 * BLK_OBS_WARPS)
 blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, int8_t *__restrict__ board,
                       uint8_t *__restrict__ pieces, int32_t *__restrict__ score, int32_t *__restrict__ meta) {
     __shared__ uint32_t sst[BLK_OBS_WARPS][BLK_WORDS];
+    __shared__ __align__(16) uint32_t stage[BLK_OBS_WARPS][100];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long g = (long long)blockIdx.x * BLK_OBS_WARPS + wid;
     if (g >= B) return;
@@ -536,19 +543,51 @@ blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, in
     }
     __syncwarp();
     if (player == -2) player = (int)(s[85] >> 8 & 3u);
-    for (int idx = lane; idx < 400; idx += 32) {
-        const int i = idx / 20, j = idx - i * 20;
-        int si = i, sj = j;                                 // source cell of np.rot90(k=-player)
-        if (player == 1) { si = 19 - j; sj = i; }
-        else if (player == 2) { si = 19 - i; sj = 19 - j; }
-        else if (player == 3) { si = j; sj = 19 - i; }
-        int v = -1;
+    const bool rel = player >= 0;
+    // 1. label planes of source row `lane`
+    uint32_t x0 = 0u, x1 = 0u, x2 = 0u, occ = 0u;
+    if (lane < 20) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) v = (s[20 * c + si] >> sj & 1u) ? c : v;
-        if (player >= 0) v = v < 0 ? -1 : ((v - player) & 3);   // _relative_player_id (:46-50)
-        else v = v + 1;
-        board[g * 400 + idx] = (int8_t)v;
+        for (int c = 0; c < 4; c++) {
+            const uint32_t row = s[20 * c + lane];
+            const int code = rel ? ((c - player) & 3) : c + 1;
+            x0 |= (code & 1) ? row : 0u;
+            x1 |= (code & 2) ? row : 0u;
+            x2 |= (code & 4) ? row : 0u;
+            occ |= row;
+        }
     }
+    const uint32_t xe = lane < 20 ? ~occ & BLK_ROWMASK : 0u;
+    // 2. source row -> 20 int8 cells (5 words);  3. np.rot90(k=-player): source cell (y, x) lands at
+    //    player 0 / absolute: (y, x)    1: (x, 19 - y)    2: (19 - y, 19 - x)    3: (19 - x, y)
+    //    i.e. at byte  base + stride * x  of the staging tile, with base and stride constants of the lane
+    if (lane < 20) {
+        const uint32_t emp = rel ? 255u : 0u;
+        uint32_t w[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const uint32_t b0 = (((x0 >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+            const uint32_t b1 = (((x1 >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+            const uint32_t b2 = (((x2 >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+            const uint32_t be = (((xe >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+            w[q] = b0 + 2u * b1 + 4u * b2 + emp * be;
+        }
+        if (player <= 0) {
+            uint32_t *o = stage[wid] + 5 * lane;
+#pragma unroll
+            for (int q = 0; q < 5; q++) o[q] = w[q];
+        } else {
+            const int base = player == 1 ? 19 - lane : player == 2 ? 20 * (19 - lane) + 19 : 380 + lane;
+            const int stride = player == 1 ? 20 : player == 2 ? -1 : -20;
+            uint8_t *o = (uint8_t *)stage[wid] + base;
+#pragma unroll
+            for (int q = 0; q < 5; q++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) o[stride * (4 * q + i)] = (uint8_t)(w[q] >> (8 * i));
+        }
+    }
+    __syncwarp();
+    if (lane < 25) ((uint4 *)(board + g * 400))[lane] = ((const uint4 *)stage[wid])[lane];
     for (int idx = lane; idx < 84; idx += 32) {             // pieces[rel][piece]
         const int r = idx / 21, p = idx - r * 21;
         const int src = player >= 0 ? ((r + player) & 3) : r;
