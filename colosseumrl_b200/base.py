@@ -51,7 +51,10 @@ class HostStepper:
         if step is None:
             def step(dev_actions):
                 return env.step_(state, dev_actions, out=state).result
-        dev_result = step(self._dev_actions)                    # allocates the record; warms the launch path
+        # the graph below bakes in the addresses of everything `step` touches: keep the closure (and with it any
+        # buffer it owns) and the record tensor alive for as long as the graph can be replayed
+        self._step = step
+        dev_result = self._dev_result = step(self._dev_actions)   # allocates the record; warms the launch path
         self.result = torch.empty(dev_result.shape, dtype=torch.uint8).pin_memory()
         self.result_np = self.result.numpy()                    # zero-copy numpy view of the pinned record (cheap reads)
         self.actions_np = self.actions.numpy()

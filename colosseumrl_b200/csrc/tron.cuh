@@ -388,7 +388,15 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
     const bool valid = t < n;
     const uint32_t lane_const = TRON_STAT_LANE[t & 31];
     pdl_wait();                  // (programmatic dependent launch only) everything above overlapped the previous kernel's tail
-    const uint32_t a = valid ? actions[e0 + t] : 0u;       // in flight together with the tile
+    uint32_t a = 0u;                                         // in flight together with the tile
+    if (valid) {
+        if (flags & CRL_FLAG_PACKED_ACTIONS) {               // one byte per environment, 2 bits per player
+            const uint32_t b = ((const uint8_t *)actions)[e0 + t];
+            a = (b & 3u) | (b & 0xcu) << 6 | (b & 0x30u) << 12 | (b & 0xc0u) << 18;
+        } else {
+            a = actions[e0 + t];
+        }
+    }
     tron_tile_load_issue(tile, bar, &maps, in, B, e0, n);
     TronOut o;
     tron_zero_out(o);

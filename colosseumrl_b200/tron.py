@@ -101,23 +101,34 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
                                             self.num_players, self.flags, self._stream))
         return new
 
-    def host_stepper(self, state: TronBatchState, stream=None, compact: bool = False):
+    def host_stepper(self, state: TronBatchState, stream=None, compact: bool = False, packed_actions: bool = False):
         """Graph-fused H2D actions -> step -> D2H result for host-side policies (see base.HostStepper).
         compact=True: the step writes the 4-byte record (CRL_FLAG_COMPACT_RESULT: terminal | alive | winners | ranking),
         which halves the PCIe read-back; `decode_compact` rebuilds the reference's return values from it on the host.
-        NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
+        packed_actions=True: the pinned action buffer is uint8 [B], 2 bits per player (`pack_actions`), a quarter of
+        the PCIe upload.  NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
         from .base import HostStepper
-        if not compact:
+        if not compact and not packed_actions:
             return HostStepper(self, state, (self.batch, 4), torch.int8, stream=stream)
-        rec = torch.empty((self.batch, 4), dtype=torch.uint8, device=self.device)
+        rec = torch.empty((self.batch, 4 if compact else 8), dtype=torch.uint8, device=self.device)
+        flags = self.flags | (_lib.FLAG_COMPACT_RESULT if compact else 0) | (_lib.FLAG_PACKED_ACTIONS if packed_actions else 0)
 
         def step(dev_actions):
             self._check(self._lib.crl_tron_step(state.packed.data_ptr(), state.packed.data_ptr(), dev_actions.data_ptr(),
                                                 rec.data_ptr(), self._stats_ptr, self.batch, self.N, self.num_players,
-                                                self.flags | _lib.FLAG_COMPACT_RESULT, self._stream))
+                                                flags, self._stream))
             state.result = None                 # the full record of an earlier step no longer describes `state`
             return rec
+        if packed_actions:
+            return HostStepper(self, state, (self.batch,), torch.uint8, stream=stream, step=step)
         return HostStepper(self, state, (self.batch, 4), torch.int8, stream=stream, step=step)
+
+    @staticmethod
+    def pack_actions(actions):
+        """int8 [B, 4] actions (0 forward, 1 right, -1 left) -> uint8 [B], player p in bits 2p..2p+1 (numpy, host side)."""
+        import numpy as np
+        a = np.asarray(actions).astype(np.uint8) & 3
+        return (a[:, 0] | a[:, 1] << 2 | a[:, 2] << 4 | a[:, 3] << 6).astype(np.uint8)
 
     def decode_compact(self, rec):
         """The reference's next_state return values from compact records (numpy uint8 [B, 4], e.g. HostStepper.wait()):

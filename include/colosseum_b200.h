@@ -35,6 +35,7 @@ extern "C" {
 
 #define CRL_FLAG_AUTO_RESET 1 /* an environment whose stored terminal flag is set is replaced by new_state() before the step */
 #define CRL_FLAG_COMPACT_RESULT 2 /* crl_tron_step only: write the 4-byte record (below) instead of the 8-byte one */
+#define CRL_FLAG_PACKED_ACTIONS 4 /* crl_tron_step only: actions are uint8[B], 2 bits per player (action & 3) */
 
 /* statistics buffer: int64[CRL_STAT_ROWS][CRL_NSTAT] on the device, accumulated (+=) by step / rollout kernels.
  * CTAs spread their partial sums over the rows so that same-address L2 atomics do not serialise; the value of
@@ -68,7 +69,8 @@ int crl_philox_words(uint32_t *out, uint64_t seed, uint64_t first_env, uint32_t 
  * Packed state: 208 bytes per environment, SoA [13][B] of 16-byte vectors (csrc/tron.cuh).
  * Supported: 5 <= N <= 19 (N*N <= 384), 2 <= P <= 4.
  * actions: int8[B][4]  (0 forward, +1 right, -1 left; TronGridEnvironment.STRING_TO_ACTION :62-67),
- *          entries of dead / absent players are ignored.
+ *          entries of dead / absent players are ignored.  With CRL_FLAG_PACKED_ACTIONS: uint8[B], player p's
+ *          action in bits 2p..2p+1 as (action & 3), i.e. 0 forward, 1 right, 3 left -- a quarter of the PCIe bytes.
  * result:  8 bytes per environment: int8 reward[4] | u8 terminal | u8 alive mask | u8 winners mask |
  *          u8 ranking (2 bits per player, competition ranking of compute_ranking).
  *          With CRL_FLAG_COMPACT_RESULT: 4 bytes per environment = the second half of that record (terminal | alive |

@@ -239,3 +239,27 @@ def case_compact_result(be, N=19, P=4, B=300, K=40, seed=9):
         assert (rewards == r8[:, :P].view(np.int8)).all(), t
         seen_terminal += int(r4[:, 0].sum())
     assert seen_terminal > 0
+
+
+def case_packed_actions(be, N=19, P=4, B=300, K=30, seed=11):
+    """CRL_FLAG_PACKED_ACTIONS: uint8 [B] with 2 bits per player gives the same states and records as int8 [B, 4]."""
+    rng = np.random.RandomState(seed)
+    full = be.zeros((13, B, 4), np.int32)
+    be.check(be.lib.crl_tron_reset(be.ptr(full), None, B, N, P, be.stream))
+    pk = be.zeros((13, B, 4), np.int32)
+    be.check(be.lib.crl_tron_reset(be.ptr(pk), None, B, N, P, be.stream))
+    for t in range(K):
+        act = rng.randint(-1, 2, size=(B, 4)).astype(np.int8)
+        a8 = act.astype(np.uint8) & 3
+        packed = (a8[:, 0] | a8[:, 1] << 2 | a8[:, 2] << 4 | a8[:, 3] << 6).astype(np.uint8)
+        a, ap = be.upload(act), be.upload(packed)
+        r1, r2 = be.zeros((B, 8), np.uint8), be.zeros((B, 8), np.uint8)
+        prev = be.upload(be.download(full))
+        be.check(be.lib.crl_tron_step(be.ptr(full), be.ptr(full), be.ptr(a), be.ptr(r1), None, B, N, P, 1, be.stream))
+        be.check(be.lib.crl_tron_step(be.ptr(pk), be.ptr(pk), be.ptr(ap), be.ptr(r2), None, B, N, P, 1 | 4, be.stream))
+        assert (be.download(r1) == be.download(r2)).all(), t
+        assert (be.download(full) == be.download(pk)).all(), t
+        # both flags together, out of place
+        r3, out3 = be.zeros((B, 4), np.uint8), be.zeros((13, B, 4), np.int32)
+        be.check(be.lib.crl_tron_step(be.ptr(prev), be.ptr(out3), be.ptr(ap), be.ptr(r3), None, B, N, P, 1 | 2 | 4, be.stream))
+        assert (be.download(r3) == be.download(r1)[:, 4:]).all() and (be.download(out3) == be.download(full)).all(), t

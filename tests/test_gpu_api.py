@@ -154,16 +154,16 @@ def test_compact_host_stepper():
     b_env = BatchedTronGridEnvironment("", batch=B, seed=4, auto_reset=True)
     sa, _ = a_env.new_state()
     sb, _ = b_env.new_state()
-    stepper = b_env.host_stepper(sb, compact=True)         # warm-up applies one all-forward step
+    stepper = b_env.host_stepper(sb, compact=True, packed_actions=True)   # warm-up applies one all-forward step
     sa, *_ = a_env.next_state(sa, None, torch.zeros((B, 4), dtype=torch.int8))
     rng = np.random.RandomState(1)
     terminals = 0
     for t in range(40):
         a = rng.randint(-1, 2, size=(B, 4)).astype(np.int8)
         sa, pa, ra, ta, wa = a_env.next_state(sa, None, torch.from_numpy(a))
-        stepper.actions_np[...] = a
+        stepper.actions_np[...] = b_env.pack_actions(a)
         rec = stepper()
-        assert rec.shape == (B, 4)
+        assert rec.shape == (B, 4) and stepper.actions_np.shape == (B,)
         alive, rewards, terminal, winners, ranking = b_env.decode_compact(rec)
         assert (alive == pa.cpu().numpy()).all() and (rewards == ra.cpu().numpy()).all()
         assert (terminal == ta.cpu().numpy()).all() and (winners == wa.cpu().numpy()).all()

@@ -43,3 +43,7 @@ def test_errors(be):
 
 def test_compact_result(be):
     cases.case_compact_result(be)
+
+
+def test_packed_actions(be):
+    cases.case_packed_actions(be)
