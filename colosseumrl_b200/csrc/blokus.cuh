@@ -13,7 +13,13 @@
 //   w[20*c + y]  row y of colour c's plane, bit x set iff colour c occupies (x, y)           (c = 0..3, 80 words)
 //   w[80 + c]    inventory of player c, bit p set iff piece p (PIECE_TYPES order) is still held
 //   w[84]        scores, one byte per player        w[85] round | mover << 8 | terminal << 16
-//   w[86]        steps taken in this episode        w[87] unused
+//   w[86]        steps taken in this episode
+//   w[87]        bit q: player q is known to have no legal move any more (a cache, 0 = unknown).  Once a player
+//                who is not the mover has no move in a round >= 1 he never has one again: his cells and pieces do not
+//                change while he cannot move and the empty cells only shrink, so the anchor set and every FIT board can
+//                only lose bits.  (Not in round 0, where the anchor is the corner; not for the mover, whose terminal test
+//                runs on the board BEFORE his own move, BlokusEnvironment.py:424.)  The step kernel sets the bit instead
+//                of repeating the full negative test every step, the legal kernel answers "no moves" from it.
 // Lanes 0..21 of the warp move the game with one 128-bit access each (352 contiguous bytes).
 //
 // Legality in bitboard form: with
@@ -348,16 +354,21 @@ blokus_legal_kernel(const uint4 *__restrict__ st, int32_t *__restrict__ counts, 
     const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
     if (g < B) {
         BlkSmem &sm = smem[wid];
-        blk_zero_fit(sm, lane);
         blk_load(sm, st, g, lane);
         if ((flags & CRL_FLAG_AUTO_RESET) && (sm.st[85] >> 16 & 1u)) blk_new_state(sm, lane);
         const uint32_t meta = sm.st[85];
         const int c = player >= 0 ? player : (int)(meta >> 8 & 3u);
+        const bool stuck = (sm.st[87] >> c & 1u) != 0u;       // cached by the step kernel: no move any more
         int32_t *out = ids + g * cap;
 #ifndef CRL_HOSTSIM
         asm volatile("" : "+l"(out));         // keep the game's list base in one register pair: a store is IMAD.WIDE + STG
 #endif
-        const int n = blk_enumerate(sm, c, (int)(meta & 0xffu), sm.st[80 + c], lane, out, cap);
+        int n = 0;
+        if (!stuck) {
+            blk_zero_fit(sm, lane);
+            __syncwarp();
+            n = blk_enumerate(sm, c, (int)(meta & 0xffu), sm.st[80 + c], lane, out, cap);
+        }
         if (lane == 0) {
             counts[g] = n;
             if (stats) atomicAdd(&sm_stat[ST_NVALID], n);
@@ -435,13 +446,16 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
         // `any` is order-independent; start with the players that have not moved yet this round (in round 0 the
         // ones that already moved have an occupied corner and would need a full, fruitless scan) and end with the mover.
         int any = 0;
+        uint32_t stuck = sm.st[87] & 15u;
 #pragma unroll 1
         for (int j = 1; j <= 4 && !any; j++) {
             const int q = (mover + j) & 3;
+            if (stuck >> q & 1u) continue;                                          // known: no move any more
             uint32_t iq = 0;
 #pragma unroll
             for (int r = 0; r < 4; r++) iq |= (r == q) ? inv[r] : 0u;
             any = blk_any_move(sm, q, round, iq, lane, zeroed);
+            if (!any && j < 4 && round >= 1) stuck |= 1u << q;                      // (see the layout comment, w[87])
         }
         const int terminal = !any;
         int reward = 0, winners = 0;
@@ -466,6 +480,7 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
         if (lane == 4) sm.st[84] = scores;
         if (lane == 5) sm.st[85] = (uint32_t)(nround & 0xff) | (uint32_t)nmover << 8 | (uint32_t)terminal << 16;
         if (lane == 6) sm.st[86] = ep_len;
+        if (lane == 7) sm.st[87] = stuck;
         blk_store(sm, outst, g, lane);
         if (lane == 0) {
             const uint32_t rank = 0xfu & ~(uint32_t)winners;
