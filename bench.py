@@ -444,7 +444,7 @@ def run_b200(args):
 
     # for the report only (untimed as far as the contract goes, it doubles as warm-up): the same steps as ONE dependent
     # chain, i.e. every launch waits for its predecessor
-    serial = None
+    serial, Ks = None, 0
     if S > 1:
         Ks = min(K, 400)
         gs = capture(k, Ks, 1)
@@ -528,7 +528,7 @@ def run_b200(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         line = {
             "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": max(W, G), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(W, G) + (Ks if serial is not None else 0), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64" if args.workload == "tron" else "u32", "data": "synthetic",
             "config": {"workload": wl["desc"], "batch_per_gpu": B, "policy": "philox4x32-10 uniform random, auto-reset",
                        "l2": "inputs larger than L2: %d independent replicas of the batch per GPU (%.0f MB of state) "
