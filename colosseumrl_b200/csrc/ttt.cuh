@@ -242,6 +242,32 @@ __global__ void ttt_policy_random_kernel(const uint4 *__restrict__ st, int8_t *_
     if (valid) actions[e] = (int8_t)a;
 }
 
+// One fused random-policy step of a NON-terminal environment (the rollout resets terminal ones first): a non-terminal
+// board has an empty cell and no winner, so the chosen cell is always free and always placed -- next_state
+// (tictactoe_2p_env.py:283-315) without its validity branches, sharing the empty mask with the policy.
+template <int NP>
+__device__ __forceinline__ void ttt_policy_step(TTTEnv &s, uint32_t r0, uint32_t rcp_lane, TTTOut &o) {
+    constexpr uint32_t CELLMASK = TTTGeo<NP>::CELLMASK;
+    const uint32_t occ = s.m[0] | s.m[1] | s.m[2] | s.m[3], empty = ~occ & CELLMASK;
+    const int n = __popc(empty);                                     // >= 1
+    const uint32_t bit = 1u << ttt_kth_bit(empty, (int)ttt_mod_small(r0, (uint32_t)max(n, 1), rcp_lane));
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        s.m[p] |= (p == s.mover) ? bit : 0u;
+        mine |= (p == s.mover) ? s.m[p] : 0u;
+    }
+    const bool win = TTTGeo<NP>::win(mine) != 0u;
+    s.winner1 = win ? s.mover + 1 : 0;
+    o.nvalid = n; o.error = 0; o.placed = 1;
+    o.reward = win ? 1 : 0;
+    o.winners = win ? 1 << s.mover : 0;
+    o.terminal = (win || (occ | bit) == CELLMASK) ? 1 : 0;
+    o.valid_after = ~(occ | bit) & CELLMASK;
+    s.mover = (s.mover + 1 == NP) ? 0 : s.mover + 1;
+    s.ep_len += 1;
+}
+
 // K fused random-policy steps with auto-reset; grid-stride like the step kernel (a thread owns <= TTT_ACC_MAX
 // environments and keeps one of them in registers for the K steps).
 template <int NP>
@@ -267,7 +293,7 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
             if (ttt_is_terminal<NP>(s)) ttt_new_state(s);
             const uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TTT);
             const int mover = s.mover;
-            ttt_step_env<NP>(s, ttt_random_action<NP>(s, r.x, rcp_lane), o);
+            ttt_policy_step<NP>(s, r.x, rcp_lane, o);
             if (stats && valid) acc.add<NP>(o, mover, s.ep_len);
             if (stats && ++pending == TTT_ACC_MAX) { acc.flush<NP>(sm_stat, lane_const); pending = 0; }
         }
