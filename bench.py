@@ -137,6 +137,39 @@ def cpu_baseline(workload, target_s=12.0):
             "sample": "%d envs x %d steps (%.1f s) of the C oracle port of the reference's Python, %d pthreads" % (B, K, dt, cores)}
 
 
+def _reference_cython_core(seconds=2.0):
+    """The reference's OWN compiled step (CyTronGrid.next_state_inplace, built from its .pyx into oracle/_ref/ in the
+    build container) driven one environment at a time by a Python loop, the way TronGridEnvironment.next_state drives
+    it -- reported next to the C port so that the port's speed is not mistaken for the reference's.  None if the
+    module did not travel."""
+    import glob
+    import importlib.util
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "CyTronGrid*.so"))
+    if not so:
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("CyTronGrid", so[0])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        from oracle import oracle as orc
+        fresh = [np.ascontiguousarray(x, dtype=np.int64) for x in orc.tron_new_state(19, 4)[:4]]
+        board, heads, dirs, deaths = [x.copy() for x in fresh]
+        acts = np.random.RandomState(0).randint(-1, 2, size=(4096, 4)).astype(np.int64)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for i in range(4096):
+                mod.next_state_inplace(board, heads, dirs, deaths, acts[i])
+                if np.count_nonzero(deaths) >= 3:
+                    board, heads, dirs, deaths = [x.copy() for x in fresh]
+            n += 4096
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "env-steps/s", "cores": 1,
+                "what": "the reference's own CyTronGrid.next_state_inplace (oracle/_ref, compiled from its .pyx) in a Python "
+                        "loop over single environments, %d steps in %.1f s" % (n, dt)}
+    except Exception as e:                               # informational only
+        return {"unavailable": repr(e)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port, all host threads), same config / metric / step."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -165,6 +198,10 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": "%d envs x %d steps" % (B, args.steps)},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.workload == "tron":
+        core = _reference_cython_core()
+        if core is not None:
+            line["reference_cython_core"] = core
     print(json.dumps(line), file=REAL_STDOUT, flush=True)
 
 
