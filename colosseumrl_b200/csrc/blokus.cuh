@@ -29,7 +29,7 @@
 //   FIT_s[q] = AND_i A[q + cell_i(s)]                       shape s fits with its bounding-box corner at q
 // action (piece, anchor a, orientation o, shift k) is legal  <=>  a in ANC  and  FIT_s[a - cell_k(s)],
 // s = shape(piece, o).  The list is emitted in the reference's order piece -> anchor (row-major) -> o -> k, with
-// lanes = the (o, k) ids of one piece and __ballot_sync / __popc prefix sums for the compaction.
+// lanes = (anchor of a group of four, orientation), a SWAR popcount + one shuffle scan per 16 anchors (blk_emit_piece).
 //
 // FIT boards: the 91 oriented shapes are exactly the fixed polyominoes of 1..5 cells, so each is a smaller one plus
 // a cell and FIT_s[q] = FIT_parent[q + off] & A[q + c].  The tree is evaluated level by level with LANES = SHAPES:
