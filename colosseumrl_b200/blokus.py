@@ -119,10 +119,14 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         return counts, ids
 
     def is_valid_action(self, state: BlokusBatchState, player: int, action) -> torch.Tensor:
+        """is_valid_action (:667-719): uint8 [B], 1 iff action[g] is in `player`'s valid list (-1 / '' is not).
+        One crl_blokus_is_valid launch: the id is tested against the allowed / anchor boards, no list is built."""
         action = self._dev(action, torch.int32)
-        counts, ids = self.valid_actions(state, player, count_stats=False)
-        slot = torch.arange(ids.shape[1], device=self.device)[None]
-        return (((ids == action[:, None]) & (slot < counts[:, None])).any(dim=1) & (action >= 0)).to(torch.uint8)
+        valid = torch.empty((self.batch,), dtype=torch.uint8, device=self.device)
+        self._check(self._lib.crl_blokus_is_valid(state.packed.data_ptr(), -1 if player is None else int(player),
+                                                  action.data_ptr(), valid.data_ptr(), self.batch, self.flags,
+                                                  self._stream))
+        return valid
 
     def player_perspective_valid_actions(self, state: BlokusBatchState, player: int):
         """player_perspective_valid_actions (:502-551): the valid list of `player`, same order, every id rotated into

@@ -342,6 +342,56 @@ __device__ __forceinline__ int blk_enumerate(BlkSmem &sm, int c, int round, uint
     return base;
 }
 
+// Is action id `aid` a legal move of player c holding `minv` on the board in sm.st?  (== membership in the valid
+// list: the piece is held, the anchor is an anchor, every cell of the placement is allowed.)  Warp-uniform result;
+// `add` receives the lane's row of the placement, `pc` / `size` the piece.  Leaves sm.A / sm.anc of player c behind.
+__device__ __forceinline__ bool blk_validate(BlkSmem &sm, int c, int round, uint32_t minv, int aid, int lane,
+                                             uint32_t &add, int &pc, int &size) {
+    // decode ((piece*400 + y*20 + x)*8 + o)*5 + k   (string form: BlokusEnvironment.py:55-106)
+    const int piece = aid / 16000, rem = aid - piece * 16000, cell = rem / 40, ok = rem - cell * 40;
+    const int o = ok / 5, k = ok - o * 5;
+    bool legal = aid >= 0 && piece < BLK_NPIECE;
+    pc = legal ? piece : 0;
+    size = BLK_PIECE_SIZE[pc];
+    legal = legal && k < size && (minv >> pc & 1u);
+    const uint32_t e = BLK_ID_TAB[BLK_PIECE_ID0[pc] + (legal ? o * size + k : 0)];
+    const uint32_t cells = BLK_SHAPE_CELLS[e & 127u];
+    const int ay = legal ? cell / 20 : 0, ax = legal ? cell - ay * 20 : 0;
+    const int qx = ax - (int)((e >> 7) & 7u), qy = ay - (int)((e >> 10) & 7u);
+    blk_allowed_and_anchors<false>(sm, c, round, lane);              // A / ANC of the player
+    legal = legal && qx >= 0 && qy >= 0 && (sm.anc[ay] >> ax & 1u);
+    add = 0u;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const uint32_t cd = cells >> (6 * i);
+        const int x = qx + (int)(cd & 7u), y = qy + (int)((cd >> 3) & 7u);
+        // y <= 23 by construction (rows 20..23 of A are zero), x may exceed 19 -> bit not in A
+        legal = legal && x >= 0 && y >= 0 && x < 20 && (sm.A[min(max(y, 0), 23)] >> (max(x, 0) + 4) & 1u);
+        add |= (y == lane && x >= 0 && x < 20) ? (1u << x) : 0u;
+    }
+    return legal;
+}
+
+// ---- is_valid_action (BlokusEnvironment.py:667-719): is actions[g] in the valid list of `player` (< 0: the game's
+// mover)?  '' (-1) is not.  One warp per game, no enumeration.
+__global__ void __launch_bounds__(32 * BLK_WARPS)
+blokus_is_valid_kernel(const uint4 *__restrict__ st, const int32_t *__restrict__ actions, uint8_t *__restrict__ valid,
+                       long long B, int player, int flags) {
+    __shared__ BlkSmem smem[BLK_WARPS];
+    const int lane = BLK_WARPS == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31), wid = BLK_WARPS == 1 ? 0 : (int)(threadIdx.x >> 5);
+    const long long g = (long long)blockIdx.x * BLK_WARPS + wid;
+    if (g >= B) return;
+    BlkSmem &sm = smem[wid];
+    blk_load(sm, st, g, lane);
+    if ((flags & CRL_FLAG_AUTO_RESET) && (sm.st[85] >> 16 & 1u)) blk_new_state(sm, lane);
+    const uint32_t meta = sm.st[85];
+    const int c = player >= 0 ? player : (int)(meta >> 8 & 3u);
+    uint32_t add;
+    int pc, size;
+    const bool legal = blk_validate(sm, c, (int)(meta & 0xffu), sm.st[80 + c], actions[g], lane, add, pc, size);
+    if (lane == 0) valid[g] = legal ? 1 : 0;
+}
+
 // ---- valid_actions: one warp per game.  player < 0: the game's current mover.
 __global__ void __launch_bounds__(32 * BLK_WARPS)
 blokus_legal_kernel(const uint4 *__restrict__ st, int32_t *__restrict__ counts, int32_t *__restrict__ ids, int cap,
@@ -402,30 +452,11 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
         uint32_t new_row = lane < 20 ? sm.st[20 * mover + lane] : 0u;
         int error = 0, placed = 0;
         if (aid >= 0) {
-            // decode ((piece*400 + y*20 + x)*8 + o)*5 + k   (string form: BlokusEnvironment.py:55-106)
-            const int piece = aid / 16000, rem = aid - piece * 16000, cell = rem / 40, ok = rem - cell * 40;
-            const int o = ok / 5, k = ok - o * 5;
-            bool legal = piece < BLK_NPIECE;
-            const int pc = legal ? piece : 0, size = BLK_PIECE_SIZE[pc];
-            uint32_t minv = 0;
+            uint32_t minv = 0, add;
 #pragma unroll
             for (int q = 0; q < 4; q++) minv |= (q == mover) ? inv[q] : 0u;
-            legal = legal && k < size && (minv >> pc & 1u);
-            const uint32_t e = BLK_ID_TAB[BLK_PIECE_ID0[pc] + (legal ? o * size + k : 0)];
-            const uint32_t cells = BLK_SHAPE_CELLS[e & 127u];
-            const int ay = cell / 20, ax = cell - ay * 20;
-            const int qx = ax - (int)((e >> 7) & 7u), qy = ay - (int)((e >> 10) & 7u);
-            blk_allowed_and_anchors<false>(sm, mover, round, lane);      // validation against A / ANC of the mover
-            legal = legal && qx >= 0 && qy >= 0 && (sm.anc[ay] >> ax & 1u);
-            uint32_t add = 0;
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                const uint32_t cd = cells >> (6 * i);
-                const int x = qx + (int)(cd & 7u), y = qy + (int)((cd >> 3) & 7u);
-                // y <= 23 by construction (rows 20..23 of A are zero), x may exceed 19 -> bit not in A
-                legal = legal && x >= 0 && y >= 0 && x < 20 && (sm.A[min(max(y, 0), 23)] >> (max(x, 0) + 4) & 1u);
-                add |= (y == lane && x >= 0 && x < 20) ? (1u << x) : 0u;
-            }
+            int pc, size;
+            const bool legal = blk_validate(sm, mover, round, minv, aid, lane, add, pc, size);
             if (legal) {
                 placed = 1;
                 new_row |= add;                                                     // Board.update_board

@@ -500,6 +500,15 @@ int crl_blokus_step(const void *state_in, void *state_out, const int32_t *action
     return check_launch("blokus_step_kernel");
 }
 
+int crl_blokus_is_valid(const void *state, int player, const int32_t *actions, uint8_t *valid, int64_t B, int flags,
+                        crl_stream_t stream) {
+    if (!state || !actions || !valid || B < 0 || player > 3) return fail(CRL_ERR_ARG, "crl_blokus_is_valid: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(blokus_is_valid_kernel, blocks_for(B, BLK_WARPS), 32 * BLK_WARPS, (cudaStream_t)stream, (const uint4 *)state,
+               actions, valid, (long long)B, player, flags);
+    return check_launch("blokus_is_valid_kernel");
+}
+
 int crl_blokus_policy_random(const int32_t *counts, const int32_t *action_ids, int32_t capacity, int32_t *actions,
                              uint64_t seed, uint64_t first_env, uint32_t step, int64_t B, crl_stream_t stream) {
     if (!counts || !action_ids || !actions || capacity <= 0 || B < 0) return fail(CRL_ERR_ARG, "crl_blokus_policy_random: bad argument%s");

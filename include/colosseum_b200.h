@@ -153,6 +153,10 @@ int crl_blokus_reset(void *state, const uint8_t *mask_or_null, int64_t B, crl_st
  * reset it to.  stats (optional): CRL_ST_NVALID += counts. */
 int crl_blokus_legal(const void *state, int player, int32_t *counts, int32_t *action_ids, int32_t capacity,
                      int64_t *stats_or_null, int64_t B, int flags, crl_stream_t stream);
+/* is_valid_action (BlokusEnvironment.py:667-719) for `player` (< 0: each game's current mover): valid[g] = 1 iff
+ * actions[g] is in that player's valid list (the pass id -1 is not), without enumerating the list. */
+int crl_blokus_is_valid(const void *state, int player, const int32_t *actions, uint8_t *valid, int64_t B, int flags,
+                        crl_stream_t stream);
 /* next_state (BlokusEnvironment.py:357-451): apply (board.py:87-98, ai.py:44-54), the lagged terminal test
  * (:424: old board, old round, new inventories), winners / reward (:425-440), round / mover advance (:446-449).
  * Unlike the reference (which applies any string blindly) an id that is not in the mover's valid list sets the

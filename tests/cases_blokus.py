@@ -191,6 +191,50 @@ def case_reset_and_capacity(be):
     assert be.lib.crl_blokus_legal(be.ptr(st), 4, be.ptr(st), be.ptr(st), 10, None, B, 0, be.stream) == 1
 
 
+def blk_is_valid(be, st, acts, player=-1, flags=0):
+    B = st.shape[0]
+    a, v = be.upload(np.ascontiguousarray(acts, np.int32)), be.zeros((B,), np.uint8)
+    be.check(be.lib.crl_blokus_is_valid(be.ptr(st), player, be.ptr(a), be.ptr(v), B, flags, be.stream))
+    return be.download(v).astype(bool)
+
+
+def case_is_valid(be, stride=2, seed=5):
+    """is_valid_action (BlokusEnvironment.py:667-719) == membership in the ordered valid list, for every seat of the
+    reference's recorded positions: listed ids, their neighbours in id space, arbitrary and out-of-range ids, ''."""
+    g = np.load(os.path.join(GOLDEN, "blokus_games.npz"))
+    board, inv, scores, rounds = _golden_prev(g)
+    sel = np.arange(0, len(g["t"]), stride)
+    st = blk_pack(be, board[sel], inv[sel], scores[sel], rounds[sel], g["mover"][sel])
+    rng = np.random.RandomState(seed)
+    n_true = n_false = 0
+    for p in (-1, 0, 1, 2, 3):
+        counts, ids = blk_legal(be, st, player=p, cap=4096)
+        for rep in range(5):
+            acts = np.zeros(len(sel), np.int32)
+            exp = np.zeros(len(sel), bool)
+            for i in range(len(sel)):
+                valid = set(ids[i, :counts[i]].tolist())
+                kind = (i + rep) % 5
+                if kind == 0 and counts[i]:
+                    a = int(ids[i, rng.randint(counts[i])])
+                elif kind == 1 and counts[i]:
+                    a = int(ids[i, rng.randint(counts[i])]) + int(rng.choice([-40, -5, -1, 1, 5, 40, 800, -800, 16000]))
+                elif kind == 2:
+                    a = int(rng.randint(0, 21 * 16000))
+                elif kind == 3:
+                    a = int(rng.choice([-1, -2, 21 * 16000, 21 * 16000 + 7, 2 ** 31 - 1, -2 ** 31, 336000 - 1]))
+                else:
+                    # a held piece on a real anchor with a random orientation / shift: the most likely near miss
+                    a = (int(ids[i, rng.randint(counts[i])]) // 40) * 40 + int(rng.randint(40)) if counts[i] else 0
+                acts[i] = a
+                exp[i] = a in valid
+            got = blk_is_valid(be, st, acts, player=p)
+            assert (got == exp).all(), (p, rep, np.flatnonzero(got != exp)[:5], acts[got != exp][:5])
+            n_true += int(exp.sum())
+            n_false += int((~exp).sum())
+    assert n_true > 100 and n_false > 100
+
+
 def case_random_boards(be, n=96, seed=11):
     """Hand-built (not necessarily reachable) positions: random colour blobs, random inventories, random round and
     mover.  valid_actions for every seat and next_state of a random legal / pass action vs the oracle."""

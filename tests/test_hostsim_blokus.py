@@ -32,3 +32,7 @@ def test_random_boards(be):
 
 def test_many_anchors(be):
     cases.case_many_anchors(be)
+
+
+def test_is_valid(be):
+    cases.case_is_valid(be, stride=6)
