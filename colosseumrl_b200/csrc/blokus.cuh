@@ -257,12 +257,13 @@ __device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int 
     // nemask: the non-empty flags the piece's table entries index (`ne`, or its pentomino group's `ne5`)
     const int n = PENT ? 5 : (int)BLK_PIECE_SIZE[p];
     const int o = lane & 7, a = lane >> 3;
-    const uint16_t *e = BLK_ORIENT_TAB_G[p * 8 + o];
-    const bool v = (nemask >> e[10] & 1u) != 0u;
+    const uint4 *e = BLK_ORIENT_TAB_G[p * 8 + o];
+    const uint4 e0 = e[0], e1 = e[1], e2 = e[2];
+    const bool v = (nemask >> e2.z & 1u) != 0u;
     if (!__any_sync(0xffffffffu, v)) return base;            // none of the piece's shapes fits anywhere
     const char *fb = (const char *)sm.F;
-    const uint32_t f0 = e[0], f1 = e[1], f2 = e[2], f3 = e[3], f4 = e[4];          // row offsets, bytes
-    const uint32_t c0 = e[5], c1 = e[6], c2 = e[7], c3 = e[8], c4 = e[9];          // column constants
+    const uint32_t f0 = e0.x, f1 = e0.y, f2 = e0.z, f3 = e0.w, f4 = e1.x;          // row offsets, bytes
+    const uint32_t c0 = e1.y, c1 = e1.z, c2 = e1.w, c3 = e2.x, c4 = e2.y;          // column constants
     const int val00 = p * 16000 + o * 5;
 #define BLK_TEST(fk, ck) hh = __funnelshift_r(hh, __funnelshift_r(*(const uint32_t *)(fb + ((fk) + row)), 0u, w + (ck)), 1)
 #pragma unroll 1
@@ -296,9 +297,11 @@ __device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int 
 #pragma unroll 1
         for (int g = 0; g < ng; g++) {
             const uint32_t sel = 0x4440u + (uint32_t)g;      // byte g, zero-extended
+            const int tg = (int)__byte_perm(tot, 0u, sel);
+            if (tg == 0) continue;                           // (warp-uniform) no hit on these four anchors
             uint32_t h = __byte_perm(hh, 0u, sel);
             int pos = base + (int)__byte_perm(excl, 0u, sel);
-            base += (int)__byte_perm(tot, 0u, sel);
+            base += tg;
             if (careful)                                     // drop the ids that do not fit (the count stays complete)
                 while (h != 0u && __popc(h) > max(cap - pos, 0)) h &= ~(0x80000000u >> __clz((int)h));
             const uint32_t w = sm.anch[a0 + 4 * g + a];

@@ -205,13 +205,15 @@ def emit(path):
     L.append("// directly usable (no unpacking):  [0..4] byte offset of FIT row (4 - dy_k) of the orientation's slot for shift")
     L.append("// k = 0..4 (the shape cell (dx_k, dy_k) sits on the anchor; id = o * 5 + k), [5..9] 4 - dx_k, [10] non-empty flag")
     L.append("// index (s for <= 4 cells: bit of `ne`; s - group start for pentominoes: bit of the group's `ne5`), [11] unused")
-    L.append("__device__ const uint16_t BLK_ORIENT_TAB_G[BLK_NPIECE * 8][12] = {")
+    L.append("// (32-bit entries, three 128-bit loads per lane and piece: 16-bit entries cost eleven LDG.U16)")
+    L.append("__device__ const uint4 BLK_ORIENT_TAB_G[BLK_NPIECE * 8][3] = {")
     for (pc, o, s_, cells) in ORIENTS:
         slot, flag = slot_flag(s_)
         cl = list(cells) + [cells[0]] * (5 - len(cells))
         offs = [(slot * FROWS + 4 - dy) * 4 for dx, dy in cl]
         cs = [4 - dx for dx, dy in cl]
-        L.append("    {" + ", ".join(str(v) for v in offs + cs + [flag, 0]) + "},")
+        v = offs + cs + [flag, 0]
+        L.append("    {" + ", ".join("{%d, %d, %d, %d}" % tuple(v[4 * j:4 * j + 4]) for j in range(3)) + "},")
     L.append("};")
     L.append("// Polyomino tree (see build_tree in the generator), one entry per shape, read by the lane that owns the shape")
     L.append("// (lanes = shapes of one level / pentomino group):   FIT_s[q] = FIT_parent[q + (px, py)] & A[q + (cx, cy)]")
