@@ -436,6 +436,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     B, K, W = (args.batch or wl["B"]), args.steps, args.warmup
+    if args.scaling == "strong":                     # total work fixed: the configured batch is split over the ranks
+        assert B % world == 0, "--scaling strong: the batch must divide by the number of GPUs"
+        B //= world
     per_replica = wl["state"] * B if args.workload != "blokus" else (wl["state"] + 435 * 4) * B
     G = args.replicas or max(2, -(-4 * L2_BYTES // per_replica))       # >= 4 x L2 of state per cycle
     work = {"tron": TronWL, "ttt4": TTTWL, "blokus": BlokusWL}[args.workload](dev, rank, B, G, K)
@@ -565,7 +568,7 @@ def run_b200(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         line = {
             "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": max(W, G) + (Ks if serial is not None else 0), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(W, G) + (Ks if serial is not None else 0), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u64" if args.workload == "tron" else "u32", "data": "synthetic",
             "config": {"workload": wl["desc"], "batch_per_gpu": B, "policy": "philox4x32-10 uniform random, auto-reset",
                        "l2": "inputs larger than L2: %d independent replicas of the batch per GPU (%.0f MB of state) "
@@ -619,6 +622,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stats", action="store_true", help="exploration: skip the fused episode statistics")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (exploration only)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's sweep): the configured batch PER GPU; strong: the configured "
+                         "batch split over the GPUs (SURVEY section 8e asks for both sweeps)")
     ap.add_argument("--streams", type=int, default=4, help="parallel chains of independent replicas inside the timed graph")
     ap.add_argument("--e2e-depth", type=int, default=0, help="environment batches in flight in the e2e leg (0 = default)")
     args = ap.parse_args()
