@@ -74,15 +74,15 @@ static int tron_check(int N, int P, int64_t B) {
     return CRL_OK;
 }
 
-// generate_start_positions (TronGridEnvironment.py:183-226) with ring_offset = 1 and the deterministic
-// spawn_offset = 2 of new_state (:228, :222-224).  The ring one cell in from the wall is listed row-major,
-// cut into four sides by the reference's slices, walked clockwise, split into P arcs (np.array_split) and
-// the element `len//2 + 2` (clamped) of each arc is the spawn.
-static int tron_starts(int N, int P, int32_t *heads, int32_t *dirs) {
+// generate_start_positions (TronGridEnvironment.py:183-226); new_state's defaults are ring_offset = 1 and the
+// deterministic spawn_offset = 2 (:228, :222-224: randint(o, o + 1) == o).  The ring `ring_offset` cells in from the
+// wall is listed row-major, cut into four sides by the reference's slices, walked clockwise, split into P arcs
+// (np.array_split) and the element `len//2 + spawn_offset` (clamped to the arc) of each arc is the spawn.
+static int tron_starts(int N, int P, int ring_offset, int spawn_offset, int32_t *heads, int32_t *dirs) {
     const int half = N / 2, odd = N % 2;
     const double center = -0.5 * (odd - 1);
-    const int r_in = half - 2, r_out = half - 1, side = 2 * (r_in + 1);
-    if (side <= 0) return CRL_ERR_ARG;
+    const int r_in = half - ring_offset - 1, r_out = half - ring_offset, side = 2 * (r_in + 1);
+    if (ring_offset < 0 || r_in < 0 || side <= 0) return CRL_ERR_ARG;
     std::vector<int> ring_rm;
     for (int iy = 0; iy < N; iy++)
         for (int ix = 0; ix < N; ix++) {
@@ -112,20 +112,22 @@ static int tron_starts(int N, int P, int32_t *heads, int32_t *dirs) {
         int b, s;
         arc((int)loop.size(), p, b, s);
         if (s <= 0) return CRL_ERR_ARG;
-        int i = s / 2 + 2;
-        heads[p] = loop[b + (i > s - 1 ? s - 1 : i)];
+        auto clamp = [](int i, int size) { return i < 0 ? 0 : (i > size - 1 ? size - 1 : i); };   // get_centers :216-220
+        heads[p] = loop[b + clamp(s / 2 + spawn_offset, s)];
         arc(4 * side, p, b, s);
         if (s <= 0) return CRL_ERR_ARG;
-        i = s / 2 + 2;
-        int di = b + (i > s - 1 ? s - 1 : i);
-        dirs[p] = (di / side + 2) % 4;
+        dirs[p] = ((b + clamp(s / 2 + spawn_offset, s)) / side + 2) % 4;
     }
+    for (int p = 0; p < P; p++)
+        for (int q = 0; q < p; q++)
+            if (heads[p] == heads[q]) return CRL_ERR_ARG;    // two players on one cell (degenerate ring)
     return CRL_OK;
 }
 
-static int tron_params(int N, int P, TronParams &prm) {
+static int tron_params(int N, int P, TronParams &prm, int ring_offset = 1, int spawn_offset = 2) {
     int32_t heads[4] = {0, 0, 0, 0}, dirs[4] = {0, 0, 0, 0};
-    if (tron_starts(N, P, heads, dirs) != CRL_OK) return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N/P%s");
+    if (tron_starts(N, P, ring_offset, spawn_offset, heads, dirs) != CRL_OK)
+        return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N / P / ring_offset / spawn_offset%s");
     prm.N = N; prm.P = P;
     prm.pmask = 0; prm.rkmask = (1u << (2 * P)) - 1u;
     TronHdr h;
@@ -194,23 +196,33 @@ int64_t crl_tron_state_bytes(int N, int P, int64_t B) {
     return (int64_t)TRON_VEC * 16 * B;
 }
 
-int crl_tron_start_positions(int N, int P, int32_t *heads, int32_t *directions) {
+int crl_tron_start_positions_at(int N, int P, int ring_offset, int spawn_offset, int32_t *heads, int32_t *directions) {
     int rc = tron_check(N, P, 0);
     if (rc) return rc;
     if (!heads || !directions) return fail(CRL_ERR_ARG, "crl_tron_start_positions: null pointer%s");
-    if (tron_starts(N, P, heads, directions)) return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N/P%s");
+    if (tron_starts(N, P, ring_offset, spawn_offset, heads, directions))
+        return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N / P / ring_offset / spawn_offset%s");
     return CRL_OK;
 }
 
-int crl_tron_reset(void *state, const uint8_t *mask, int64_t B, int N, int P, crl_stream_t stream) {
+int crl_tron_start_positions(int N, int P, int32_t *heads, int32_t *directions) {
+    return crl_tron_start_positions_at(N, P, 1, 2, heads, directions);
+}
+
+int crl_tron_reset_at(void *state, const uint8_t *mask, int64_t B, int N, int P, int ring_offset, int spawn_offset,
+                      crl_stream_t stream) {
     int rc = tron_check(N, P, B);
     if (rc) return rc;
     if (!state) return fail(CRL_ERR_ARG, "crl_tron_reset: null state%s");
     TronParams prm;
-    if ((rc = tron_params(N, P, prm))) return rc;
+    if ((rc = tron_params(N, P, prm, ring_offset, spawn_offset))) return rc;
     if (B == 0) return CRL_OK;
     CRL_LAUNCH(tron_reset_kernel, blocks_for(B * TRON_VEC, 256), 256, (cudaStream_t)stream, (uint4 *)state, mask, (long long)B, prm);
     return check_launch("tron_reset_kernel");
+}
+
+int crl_tron_reset(void *state, const uint8_t *mask, int64_t B, int N, int P, crl_stream_t stream) {
+    return crl_tron_reset_at(state, mask, B, N, P, 1, 2, stream);
 }
 
 int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, int64_t *stats,

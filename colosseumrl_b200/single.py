@@ -88,9 +88,12 @@ class TronGridEnvironment(SingleEnvironment):
         self.move_array = ["forward", "right", "left"]
         self._moves = np.zeros(self.num_players, np.int64)      # persists across calls like the reference's (:118)
 
-    def new_state(self, num_players: int = None):
-        st, _ = self._b.new_state(num_players)
+    def new_state(self, num_players: int = None, ring_offset: int = 1, spawn_offset=2):
+        st, _ = self._b.new_state(num_players, ring_offset, spawn_offset)
         return self._unpack(st), self.player_array
+
+    def generate_start_positions(self, ring_offset: int = 1, spawn_offset: int = 0):
+        return self._b.generate_start_positions(ring_offset, spawn_offset)
 
     def _pack(self, state):
         board, heads, directions, deaths = state

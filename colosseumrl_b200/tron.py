@@ -65,14 +65,30 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
     def _alloc(self):
         return torch.empty((13, self.batch, 4), dtype=torch.int32, device=self.device)
 
-    def new_state(self, num_players: int = None, out: Optional[TronBatchState] = None):
-        """TronGridEnvironment.new_state (:228-263) for every environment of the batch."""
+    def new_state(self, num_players: int = None, ring_offset: int = 1, spawn_offset=2,
+                  out: Optional[TronBatchState] = None):
+        """TronGridEnvironment.new_state (:228-263) for every environment of the batch.  ring_offset / spawn_offset as
+        in the reference (generate_start_positions :183-226); a (lo, hi) tuple draws ONE offset per player list entry
+        like the reference does (np.random.randint(lo, hi), :222-224) -- here a single draw shared by the players
+        and the batch, taken on the host."""
         assert num_players is None or num_players == self.num_players, \
             "Do not change the number of players from the game configuration."
+        if not isinstance(spawn_offset, int):
+            import numpy as np
+            spawn_offset = int(np.random.randint(*spawn_offset))
         packed = out.packed if out is not None else self._alloc()
-        self._check(self._lib.crl_tron_reset(packed.data_ptr(), None, self.batch, self.N, self.num_players, self._stream))
+        self._check(self._lib.crl_tron_reset_at(packed.data_ptr(), None, self.batch, self.N, self.num_players,
+                                                int(ring_offset), int(spawn_offset), self._stream))
         players = torch.full((self.batch,), (1 << self.num_players) - 1, dtype=torch.uint8, device=self.device)
         return TronBatchState(packed), players
+
+    def generate_start_positions(self, ring_offset: int = 1, spawn_offset: int = 0):
+        """generate_start_positions (:183-226): (heads = y * N + x, directions) as int64 numpy arrays."""
+        import ctypes as C
+        import numpy as np
+        h, d = (C.c_int32 * 4)(), (C.c_int32 * 4)()
+        self._check(self._lib.crl_tron_start_positions_at(self.N, self.num_players, int(ring_offset), int(spawn_offset), h, d))
+        return (np.array(h[:self.num_players], np.int64), np.array(d[:self.num_players], np.int64))
 
     def reset_where(self, state: TronBatchState, mask: torch.Tensor):
         mask = self._dev(mask, torch.uint8)

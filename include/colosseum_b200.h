@@ -83,6 +83,14 @@ int64_t crl_tron_state_bytes(int N, int P, int64_t B);
 int crl_tron_start_positions(int N, int P, int32_t *heads, int32_t *directions);
 /* new_state (TronGridEnvironment.py:228-263) for every environment, or where mask[e] != 0 */
 int crl_tron_reset(void *state, const uint8_t *mask_or_null, int64_t B, int N, int P, crl_stream_t stream);
+/* The same two with new_state's optional arguments (TronGridEnvironment.py:228: ring_offset = how far in from the wall
+ * the spawn ring lies, spawn_offset = shift of every spawn along its arc; the defaults are 1 and 2).  An integer
+ * spawn_offset is deterministic in the reference (:222-224); its random (lo, hi) tuple form is the caller's business:
+ * draw the offset on the host and pass it.  CRL_ERR_ARG if the ring is degenerate for this N / P.  Auto-reset
+ * inside the step kernels (CRL_FLAG_AUTO_RESET) always restarts from the default new_state(). */
+int crl_tron_start_positions_at(int N, int P, int ring_offset, int spawn_offset, int32_t *heads, int32_t *directions);
+int crl_tron_reset_at(void *state, const uint8_t *mask_or_null, int64_t B, int N, int P, int ring_offset, int spawn_offset,
+                      crl_stream_t stream);
 /* next_state (TronGridEnvironment.py:265-323 -> CyTronGrid.pyx:3-62) + compute_ranking (:483-508).
  * state_out may equal state_in (in place). stats may be NULL. */
 int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result,

@@ -61,6 +61,41 @@ def case_start_positions(be):
             assert (h[0][:P] == oh).all() and (h[1][:P] == od).all(), (N, P)
 
 
+def case_start_positions_golden(be):
+    """generate_start_positions for every (N, P, ring_offset, spawn_offset) recorded from the real reference
+    (tests/golden/tron_starts.npz, oracle/make_golden_starts.py), and new_state at those spawns."""
+    import ctypes as C
+    tab = np.load(os.path.join(GOLDEN, "tron_starts.npz"))["table"]
+    checked = resets = 0
+    for row in tab:
+        N, P, ring, spawn, ok = (int(v) for v in row[:5])
+        if N > 19 or not ok:
+            continue
+        h, d = np.zeros(4, np.int32), np.zeros(4, np.int32)
+        rc = be.lib.crl_tron_start_positions_at(N, P, ring, spawn, h.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                d.ctypes.data_as(C.POINTER(C.c_int32)))
+        distinct = len(set(row[5:5 + P].tolist())) == P
+        if not distinct:
+            assert rc != 0, (N, P, ring, spawn)      # two players on one cell: refused
+            continue
+        assert rc == 0, (N, P, ring, spawn, be.lib.crl_last_error())
+        assert h[:P].tolist() == row[5:5 + P].tolist() and d[:P].tolist() == row[9:9 + P].tolist(), (N, P, ring, spawn)
+        oh, od = orc.tron_start_positions(N, P, ring, spawn)
+        assert oh.tolist() == h[:P].tolist() and od.tolist() == d[:P].tolist()
+        checked += 1
+        if (N, P) in ((19, 4), (15, 4), (9, 3), (12, 2)) and spawn in (-2, 0, 3):
+            B = 5
+            st = be.zeros((13, B, 4), np.int32)
+            be.check(be.lib.crl_tron_reset_at(be.ptr(st), None, B, N, P, ring, spawn, be.stream))
+            board, heads, dirs, deaths, term = tron_unpack(be, st, N, P)
+            exp = np.zeros(N * N, np.int64)
+            exp[row[5:5 + P]] = np.arange(1, P + 1)
+            assert (board.reshape(B, -1) == exp[None]).all() and (heads == row[None, 5:5 + P]).all()
+            assert (dirs == row[None, 9:9 + P]).all() and (deaths == 0).all() and (term == 0).all()
+            resets += 1
+    assert checked > 1000 and resets > 20, (checked, resets)
+
+
 def case_reset(be):
     for N, P in [(19, 4), (9, 4), (7, 3), (8, 2), (15, 4), (19, 2), (6, 4), (5, 2)]:
         B = 70

@@ -170,3 +170,30 @@ def test_compact_host_stepper():
         assert (ranking == a_env.compute_ranking(sa).cpu().numpy()).all()
         terminals += int(terminal.sum())
     assert terminals > 0 and (sa.packed == sb.packed).all()
+
+
+def test_tron_new_state_spawn_arguments():
+    """new_state(ring_offset, spawn_offset) (TronGridEnvironment.py:228) and generate_start_positions through the Python
+    surface, batched and single-environment, against the reference-recorded table."""
+    import os
+    from colosseumrl_b200.tron import BatchedTronGridEnvironment
+    from colosseumrl_b200.single import TronGridEnvironment
+    tab = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tron_starts.npz"))["table"]
+    want = {tuple(int(v) for v in r[:4]): r for r in tab if r[4]}
+    env = BatchedTronGridEnvironment("15;4", batch=33)
+    single = TronGridEnvironment("15;4")
+    for ring, spawn in ((1, 2), (2, 0), (3, -2), (0, 3)):
+        row = want[(15, 4, ring, spawn)]
+        h, d = env.generate_start_positions(ring, spawn)
+        assert h.tolist() == row[5:9].tolist() and d.tolist() == row[9:13].tolist()
+        state, _ = env.new_state(ring_offset=ring, spawn_offset=spawn)
+        obs = env.state_to_observation(state, -1)
+        assert (obs["heads"].cpu().numpy() == row[None, 5:9]).all() and (obs["directions"].cpu().numpy() == row[None, 9:13]).all()
+        (board, heads, dirs, deaths), players = single.new_state(ring_offset=ring, spawn_offset=spawn)
+        assert heads.tolist() == row[5:9].tolist() and dirs.tolist() == row[9:13].tolist() and not deaths.any()
+        assert board.ravel()[heads].tolist() == [1, 2, 3, 4] and int((board != 0).sum()) == 4
+    # the tuple form draws an offset in [lo, hi)
+    (board, heads, dirs, deaths), _ = single.new_state(spawn_offset=(-1, 2))
+    assert any(heads.tolist() == want[(15, 4, 1, s)][5:9].tolist() for s in (-1, 0, 1))
+    with pytest.raises(Exception):
+        env.new_state(ring_offset=9)                     # no such ring on a 15 x 15 board

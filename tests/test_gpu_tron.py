@@ -55,3 +55,7 @@ def test_compact_result(be):
 
 def test_packed_actions(be):
     cases.case_packed_actions(be)
+
+
+def test_start_positions_golden(be):
+    cases.case_start_positions_golden(be)
