@@ -88,6 +88,13 @@ class TronGridEnvironment(SingleEnvironment):
         self.move_array = ["forward", "right", "left"]
         self._moves = np.zeros(self.num_players, np.int64)      # persists across calls like the reference's (:118)
 
+    @classmethod
+    def create(cls, board_size: int = 19, num_players: int = 4, observation_window: int = -1,
+               remove_on_death: bool = False, device="cuda:0") -> "TronGridEnvironment":
+        """TronGridEnvironment.create (:69-90): build the environment from options instead of a config string."""
+        from .tron import create_tron_config
+        return cls(create_tron_config(board_size, num_players, observation_window, remove_on_death), device=device)
+
     def new_state(self, num_players: int = None, ring_offset: int = 1, spawn_offset=2):
         st, _ = self._b.new_state(num_players, ring_offset, spawn_offset)
         return self._unpack(st), self.player_array
@@ -212,6 +219,19 @@ class BlokusEnvironment(SingleEnvironment):
             raise RuntimeError("valid-action list longer than the adapter's capacity (%d > %d)" % (n, ids.shape[1]))
         return [_blokus.action_to_string(int(a)) for a in self._np(ids[0, :n])]
 
+    def valid_actions_dict(self, state, player: int) -> Dict[str, Dict[tuple, List[str]]]:
+        """valid_actions_dict (:630-665) = Board.get_all_valid_moves (board.py:170-193): {piece: {(x, y): ["orientk", ...]}}
+        with the reference's insertion order (pieces in inventory order, anchors row-major, orientation, shift).
+        `valid_actions` is this dictionary flattened (:490-496), so it is rebuilt from the ordered id list."""
+        out: Dict[str, Dict[tuple, List[str]]] = {}
+        for a in self.valid_actions(state, player):
+            if a == "":
+                continue
+            piece, index, orientation = a.split(";")
+            x, y = (int(v) for v in index.strip("()").split(","))
+            out.setdefault(piece, {}).setdefault((x, y), []).append(orientation)
+        return out
+
     def player_perspective_valid_actions(self, state, player: int) -> List[str]:
         """BlokusEnvironment.py:502-551: valid actions in the frame of the player's rotated observation."""
         return [self.convert_real_action_to_player_perspective_action(a, player) for a in self.valid_actions(state, player)]
@@ -249,6 +269,11 @@ class _TicTacToe(SingleEnvironment):
     def new_state(self, num_players: int = None):
         assert num_players is None or num_players == self.max_players
         return (np.full(self._shape, -1, np.int8), None), [0]
+
+    def current_rewards(self, state) -> List[float]:
+        """current_rewards (tictactoe_2p_env.py:219-238): +1 winner / -1 everybody else once there is a winner, else 0."""
+        winner = state[1]
+        return [0 if winner is None else (1 if p == winner else -1) for p in range(self.max_players)]
 
     def _pack(self, state, mover: int):
         board, winner = state

@@ -56,6 +56,13 @@ class _BatchedTicTacToe(BatchedBaseEnvironment):
         mover = (new.packed[:, 0] >> 27) & 3
         return new, (1 << mover).to(torch.uint8), r[:, 0].view(torch.int8), r[:, 1] & 1, r[:, 2]
 
+    def current_rewards(self, state: TTTBatchState) -> torch.Tensor:
+        """current_rewards (tictactoe_2p_env.py:219-238): int8 [B, n], +1 winner / -1 the others once a game has a
+        winner, 0 before."""
+        w1 = (state.packed[:, 0] >> 29) & 7                                        # winner + 1, 0 = None
+        seat = torch.arange(self.N_PLAYERS, device=self.device, dtype=torch.int32)[None]
+        return torch.where(w1[:, None] == 0, 0, torch.where(seat + 1 == w1[:, None], 1, -1)).to(torch.int8)
+
     def step_(self, state: TTTBatchState, actions, out: Optional[TTTBatchState] = None) -> TTTBatchState:
         """The bare crl_ttt_step launch (out may be `state` itself: in place).  Outputs are in new.result / new.valid."""
         actions = self._dev(actions, torch.int8)

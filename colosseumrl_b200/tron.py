@@ -9,6 +9,11 @@ from .base import BatchedBaseEnvironment
 from . import _lib
 
 
+def create_tron_config(*args) -> str:
+    """Options -> config string "N;P;window;remove_on_death" (TronGridEnvironment.py:12-25)."""
+    return ";".join(str(a) for a in args)
+
+
 def parse_tron_config(config: str):
     """Same config string as the reference: "N;P;window;remove_on_death" (TronGridEnvironment.py:28-58)."""
     if len(config) == 0:
@@ -44,6 +49,16 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         self.N, self.num_players, self.observation_window, self.remove_on_death = parse_tron_config(config)
         if self._lib.crl_tron_state_bytes(self.N, self.num_players, self.batch) < 0:
             raise _lib.CrlError(self._lib.crl_last_error().decode())
+
+    @classmethod
+    def create(cls, board_size: int = 19, num_players: int = 4, observation_window: int = -1,
+               remove_on_death: bool = False, **kwargs) -> "BatchedTronGridEnvironment":
+        """TronGridEnvironment.create (:69-90); kwargs: batch, device, seed, auto_reset, first_env_id."""
+        return cls(create_tron_config(board_size, num_players, observation_window, remove_on_death), **kwargs)
+
+    def __repr__(self):
+        return ("BatchedTronGridEnvironment(size=%dx%d, players=%d, batch=%d, fully_observable=%s, remove_on_death=%s)"
+                % (self.N, self.N, self.num_players, self.batch, self.observation_window < 0, self.remove_on_death))
 
     @property
     def min_players(self) -> int:

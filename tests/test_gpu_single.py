@@ -170,3 +170,47 @@ def test_vector_env():
         per = [env.state_to_observation(v.state, p)["board"] for p in range(4)]
         exp = torch.stack([per[int(mover[g])][g] for g in range(128)])
         assert (obs["board"] == exp).all()
+
+
+def test_blokus_valid_actions_dict_and_current_rewards():
+    """valid_actions_dict (BlokusEnvironment.py:630-665) against dictionaries recorded from the real reference
+    (oracle/make_golden_dict.py): same keys, same insertion order, same orientation lists; TTT current_rewards."""
+    import json
+    from colosseumrl_b200.single import BlokusEnvironment, TicTacToe2PlayerEnv, TicTacToe3PlayerEnv, TicTacToe4PlayerEnv
+    from colosseumrl_b200.blokus import action_to_string
+    gold = json.load(open(os.path.join(GOLDEN, "blokus_valid_dict.json")))
+    g = np.load(os.path.join(GOLDEN, "blokus_games.npz"))
+    env = BlokusEnvironment()
+    want = {}
+    for rec in gold["blokus"]:
+        want.setdefault(rec["row"], []).append(rec)
+    state, players = env.new_state()
+    seen = 0
+    for i in np.flatnonzero(g["game"] == 0):
+        for rec in want.get(int(i), []):
+            d = env.valid_actions_dict(state, rec["player"])
+            got = [[piece, [[k[0], k[1], v] for k, v in idx.items()]] for piece, idx in d.items()]
+            assert got == rec["dict"], (i, rec["player"])
+            assert all(isinstance(k, tuple) for idx in d.values() for k in idx)
+            seen += 1
+        state, players, *_ = env.next_state(state, [int(g["mover"][i])], [action_to_string(int(g["action"][i]))])
+    assert seen == len(gold["blokus"]) >= 10
+    assert env.current_rewards(state) == [float(s) for s in g["scores"][np.flatnonzero(g["game"] == 0)[-1]]]
+    envs = {2: TicTacToe2PlayerEnv(), 3: TicTacToe3PlayerEnv(), 4: TicTacToe4PlayerEnv()}
+    for rec in gold["ttt_current_rewards"]:
+        e = envs[rec["n"]]
+        st, _ = e.new_state()
+        assert e.current_rewards((st[0], rec["winner"])) == rec["rewards"]
+        b = e._b.current_rewards(e._pack((st[0], rec["winner"]), 0)).cpu().numpy()
+        assert b[0].tolist() == rec["rewards"]
+
+
+def test_tron_create():
+    from colosseumrl_b200.single import TronGridEnvironment
+    from colosseumrl_b200.tron import BatchedTronGridEnvironment, create_tron_config, parse_tron_config
+    assert create_tron_config(15, 3, -1, False) == "15;3;-1;False"
+    assert list(parse_tron_config("15;3;-1;False")) == [15, 3, -1, False]
+    env = TronGridEnvironment.create(board_size=11, num_players=3)
+    assert env.N == 11 and env.num_players == 3 and env.observation_shape["board"] == (11, 11)
+    benv = BatchedTronGridEnvironment.create(board_size=9, num_players=2, batch=4)
+    assert benv.N == 9 and benv.num_players == 2 and "9x9" in repr(benv)
