@@ -121,10 +121,7 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
     // row-major anchor list: exclusive prefix of the per-row counts
     int cnt = __popc(an), pre = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, pre, d);
-        if (lane >= d) pre += t;
-    }
+    for (int d = 1; d < 32; d <<= 1) pre = (int)warp_scan_step((uint32_t)pre, d);
     const int total = __shfl_sync(0xffffffffu, pre, 31);
     int pos = pre - cnt;
     while (an) {
@@ -288,10 +285,7 @@ __device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int 
         cc = (cc + (cc >> 4)) & 0x0f0f0f0fu;
         uint32_t incl = cc;                                  // per-byte inclusive scan over the lanes (sums <= 160)
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
+        for (int d = 1; d < 32; d <<= 1) incl = warp_scan_step(incl, d);
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31), excl = incl - cc;
         const bool careful = base + (int)((tot * 0x01010101u) >> 24) > cap;        // rare: the caller's list is too short
 #pragma unroll 1

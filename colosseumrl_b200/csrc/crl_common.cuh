@@ -78,6 +78,21 @@ __device__ __forceinline__ void st_global_u32(int32_t *p, int32_t v) {
 #endif
 }
 
+// One step of a warp-wide inclusive scan: x += (value of lane - d) if that lane exists.  shfl.sync.up returns the
+// "source lane in range" predicate itself, so a step is SHFL + one predicated add (the C form `if (lane >= d)`
+// compiles to SHFL + ISETP + SEL + IADD).  All 32 lanes must call.
+__device__ __forceinline__ uint32_t warp_scan_step(uint32_t x, int d) {
+#ifndef CRL_HOSTSIM
+    asm volatile("{ .reg .pred p; .reg .u32 t;\n\t"
+                 "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+                 "@p add.u32 %0, %0, t; }" : "+r"(x) : "r"(d));
+    return x;
+#else
+    const uint32_t t = __shfl_up_sync(0xffffffffu, x, (unsigned)d);
+    return ((int)(threadIdx.x & 31) >= d) ? x + t : x;
+#endif
+}
+
 // ---- bulk asynchronous copies (TMA 1-D, SASS UBLKCP) between global memory and a shared-memory tile ----------
 // The SoA state layout makes every 16-byte vector of a CTA's environments one contiguous global segment, so a
 // tile is moved by a handful of bulk copies issued by ONE thread; the other threads never touch the data they
