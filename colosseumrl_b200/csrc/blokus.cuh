@@ -264,21 +264,30 @@ __device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int 
     const int val00 = p * 16000 + o * 5;
 #define BLK_TEST(fk, ck) hh = __funnelshift_r(hh, __funnelshift_r(*(const uint32_t *)(fb + ((fk) + row)), 0u, w + (ck)), 1)
 #pragma unroll 1
-    for (int a0 = 0; a0 < na; a0 += 16) {                    // chunks of four groups (one or two chunks in practice)
+    for (int a0 = 0; a0 < na; a0 += 16) {                    // chunks of four groups (one chunk in practice: ~8 anchors)
         const int ng = min(4, (na - a0 + 3) >> 2);
-        uint32_t hh = 0u;
-#pragma unroll 1
-        for (int g = 0; g < ng; g++) {
-            const uint32_t w = __byte_perm(sm.anch[a0 + 4 * g + a], 0u, 0x1440u);   // (the list is padded with never-fitting anchors)
-            const uint32_t row = w >> 25;
-            BLK_TEST(f0, c0);
-            if (n > 1) BLK_TEST(f1, c1);
-            if (n > 2) BLK_TEST(f2, c2);
-            if (n > 3) BLK_TEST(f3, c3);
-            if (n > 4) BLK_TEST(f4, c4);
-            hh >>= 8 - n;                                    // one byte per group
+        const uint16_t *al = sm.anch + a0 + a;
+        uint32_t hh = 0u, wg[4];
+        // both group loops are fully unrolled (the selectors become immediates, the anchor words stay in registers,
+        // no loop counters); groups past the end of the list are skipped by a warp-uniform test
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if (g < ng) {
+                wg[g] = al[4 * g];                           // (the list is padded with never-fitting anchors)
+                const uint32_t w = __byte_perm(wg[g], 0u, 0x1440u);
+                const uint32_t row = w >> 25;
+                BLK_TEST(f0, c0);
+                if (n > 1) BLK_TEST(f1, c1);
+                if (n > 2) BLK_TEST(f2, c2);
+                if (n > 3) BLK_TEST(f3, c3);
+                if (n > 4) BLK_TEST(f4, c4);
+                hh >>= 8 - n;                                // one byte per group
+            } else {
+                wg[g] = 0u;
+                hh >>= 8;
+            }
         }
-        hh = v ? hh >> (8 * (4 - ng)) : 0u;                  // byte g = hits of (anchor a0 + 4 g + a, o), bit k = shift k
+        hh = v ? hh : 0u;                                    // byte g = hits of (anchor a0 + 4 g + a, o), bit k = shift k
         if (!__any_sync(0xffffffffu, hh != 0u)) continue;
         uint32_t cc = hh - ((hh >> 1) & 0x55555555u);        // per-byte popcount
         cc = (cc & 0x33333333u) + ((cc >> 2) & 0x33333333u);
@@ -288,17 +297,16 @@ __device__ __forceinline__ int blk_emit_piece(BlkSmem &sm, uint32_t nemask, int 
         for (int d = 1; d < 32; d <<= 1) incl = warp_scan_step(incl, d);
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31), excl = incl - cc;
         const bool careful = base + (int)((tot * 0x01010101u) >> 24) > cap;        // rare: the caller's list is too short
-#pragma unroll 1
-        for (int g = 0; g < ng; g++) {
-            const uint32_t sel = 0x4440u + (uint32_t)g;      // byte g, zero-extended
-            const int tg = (int)__byte_perm(tot, 0u, sel);
-            if (tg == 0) continue;                           // (warp-uniform) no hit on these four anchors
-            uint32_t h = __byte_perm(hh, 0u, sel);
-            int pos = base + (int)__byte_perm(excl, 0u, sel);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int tg = (int)((tot >> (8 * g)) & 0xffu);
+            if (tg == 0) continue;                           // (warp-uniform) no hit on these four anchors / no such group
+            uint32_t h = (hh >> (8 * g)) & 0xffu;
+            int pos = base + (int)((excl >> (8 * g)) & 0xffu);
             base += tg;
             if (careful)                                     // drop the ids that do not fit (the count stays complete)
                 while (h != 0u && __popc(h) > max(cap - pos, 0)) h &= ~(0x80000000u >> __clz((int)h));
-            const uint32_t w = sm.anch[a0 + 4 * g + a];
+            const uint32_t w = wg[g];
             const int val0 = (int)(w >> 9) * 200 + (int)(w & 31u) * 40 + val00;      // (y * 20 + x) * 40 + ...
             // (32-bit running index: a 64-bit running pointer costs predicated 64-bit adds and moves per store)
             if (h & 1u) st_global_u32(out + pos++, val0);
