@@ -449,8 +449,9 @@ int crl_ttt_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed,
     if (rc) return rc;
     if (!state || B < 0 || K < 0) return fail(CRL_ERR_ARG, "crl_ttt_rollout: bad argument%s");
     if (B == 0 || K == 0) return CRL_OK;
+    const PhiloxKeys keys = philox_expand_keys((crl_u64)seed);
 #define TTT_ROLL(NP) CRL_LAUNCH(ttt_rollout_kernel<NP>, ttt_blocks(B), 256, (cudaStream_t)stream, (uint4 *)state, \
-                               (uint32_t *)result, (crl_u64 *)stats, (long long)B, (crl_u64)seed, (crl_u64)first_env, step0, K)
+                               (uint32_t *)result, (crl_u64 *)stats, (long long)B, keys, (crl_u64)first_env, step0, K)
     if (n == 2) TTT_ROLL(2); else if (n == 3) TTT_ROLL(3); else TTT_ROLL(4);
 #undef TTT_ROLL
     return check_launch("ttt_rollout_kernel");

@@ -251,12 +251,12 @@ __device__ __forceinline__ void ttt_policy_step(TTTEnv &s, uint32_t r0, uint32_t
     const uint32_t occ = s.m[0] | s.m[1] | s.m[2] | s.m[3], empty = ~occ & CELLMASK;
     const int n = __popc(empty);                                     // >= 1
     const uint32_t bit = 1u << ttt_kth_bit(empty, (int)ttt_mod_small(r0, (uint32_t)max(n, 1), rcp_lane));
-    uint32_t mine = 0u;
+    // the mover's cells: a 4:1 multiplexer on the two mover bits (3 selects), then one predicated write-back per seat
+    const bool b0 = (s.mover & 1) != 0, b1 = (s.mover & 2) != 0;
+    const uint32_t lo = b0 ? s.m[1] : s.m[0], hi = b0 ? s.m[3 % NP] : s.m[2 % NP];
+    const uint32_t mine = ((NP > 2 && b1) ? hi : lo) | bit;
 #pragma unroll
-    for (int p = 0; p < NP; p++) {
-        s.m[p] |= (p == s.mover) ? bit : 0u;
-        mine |= (p == s.mover) ? s.m[p] : 0u;
-    }
+    for (int p = 0; p < NP; p++) s.m[p] = (p == s.mover) ? mine : s.m[p];
     const bool win = TTTGeo<NP>::win(mine) != 0u;
     s.winner1 = win ? s.mover + 1 : 0;
     o.nvalid = n; o.error = 0; o.placed = 1;
@@ -264,7 +264,7 @@ __device__ __forceinline__ void ttt_policy_step(TTTEnv &s, uint32_t r0, uint32_t
     o.winners = win ? 1 << s.mover : 0;
     o.terminal = (win || (occ | bit) == CELLMASK) ? 1 : 0;
     o.valid_after = ~(occ | bit) & CELLMASK;
-    s.mover = (s.mover + 1 == NP) ? 0 : s.mover + 1;
+    s.mover = NP == 4 ? ((s.mover + 1) & 3) : ((s.mover + 1 == NP) ? 0 : s.mover + 1);
     s.ep_len += 1;
 }
 
@@ -273,7 +273,7 @@ __device__ __forceinline__ void ttt_policy_step(TTTEnv &s, uint32_t r0, uint32_t
 template <int NP>
 __global__ void __launch_bounds__(256, 8)
 ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl_u64 *stats, long long B,
-                   crl_u64 seed, crl_u64 first_env, uint32_t step0, int K) {
+                   const PhiloxKeys keys, crl_u64 first_env, uint32_t step0, int K) {
     __shared__ int sm_stat[CRL_NSTAT];
     if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
     const uint32_t lane_const = TTT_STAT_LANE[threadIdx.x & 31], rcp_lane = ttt_rcp_lane();
@@ -291,9 +291,10 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
         if (valid) ttt_decode(s, ld_stream(state + e));
         for (int k = 0; k < K; k++) {                    // (lanes past the end of the batch step a dummy board)
             if (ttt_is_terminal<NP>(s)) ttt_new_state(s);
-            const uint4 r = env_words(seed, first_env + (crl_u64)e, step0 + (uint32_t)k, CRL_TAG_TTT);
+            const crl_u64 ge = first_env + (crl_u64)e;
+            const uint32_t r0 = philox4x32_10_x((uint32_t)ge, (uint32_t)(ge >> 32), step0 + (uint32_t)k, CRL_TAG_TTT, keys);
             const int mover = s.mover;
-            ttt_policy_step<NP>(s, r.x, rcp_lane, o);
+            ttt_policy_step<NP>(s, r0, rcp_lane, o);
             if (stats && valid) acc.add<NP>(o, mover, s.ep_len);
             if (stats && ++pending == TTT_ACC_MAX) { acc.flush<NP>(sm_stat, lane_const); pending = 0; }
         }
