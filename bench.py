@@ -251,11 +251,11 @@ class TronWL:
             e.stats_rows = self.envs[0].stats_rows                      # one statistics vector per rank
         self.local_t = [0] * G
         self.actions = torch.empty((K, B, 4), dtype=torch.int8, device=dev)   # resident inputs of the timed steps
-        # e2e: the host policy hands over packed actions (uint8 per env, 2 bits per player) and reads the 4-byte record
+        # e2e: the host policy hands over packed actions (uint8 per env, 2 bits per player) and reads the 2-byte record
         self.h_actions = [torch.from_numpy(BatchedTronGridEnvironment.pack_actions(
             np.random.RandomState(rank + i).randint(-1, 2, size=(B, 4)).astype(np.int8))).pin_memory() for i in range(2)]
-        self.h2d, self.d2h = B * 1, B * 4
-        self.stepper_kwargs = {"compact": True, "packed_actions": True}
+        self.h2d, self.d2h = B * 1, B * 2
+        self.stepper_kwargs = {"compact": 2, "packed_actions": True}
         self.steppers = None
 
     def prepare(self, k0, K):

@@ -14,6 +14,7 @@ NSTAT = 32
 STAT_ROWS = 256
 FLAG_AUTO_RESET = 1
 FLAG_COMPACT_RESULT = 2      # crl_tron_step: 4-byte result record
+FLAG_COMPACT2_RESULT = 8     # crl_tron_step: 2-byte result record
 FLAG_PACKED_ACTIONS = 4      # crl_tron_step: uint8[B] actions, 2 bits per player
 
 _vp, _i64, _i32, _u64, _u32, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, C.c_int

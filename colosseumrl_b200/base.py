@@ -81,7 +81,8 @@ class HostStepper:
             raise RuntimeError("HostStepper launch failed: cudaError %d" % rc)
 
     def wait(self):
-        """Block until the launched step's result record is in `self.result` (pinned host memory)."""
+        """Block until the launched step's result record is in `self.result` (pinned host memory).  (Waiting for the
+        stepper's stream instead of an event saves a runtime call per step but measured no faster end to end.)"""
         rc = self._rt.cudaEventSynchronize(self._done)
         if rc:
             raise RuntimeError("HostStepper wait failed: cudaError %d" % rc)

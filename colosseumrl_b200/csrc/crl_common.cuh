@@ -45,6 +45,7 @@ enum {
 // step flags
 #define CRL_FLAG_AUTO_RESET 1
 #define CRL_FLAG_COMPACT_RESULT 2
+#define CRL_FLAG_COMPACT2_RESULT 8
 #define CRL_FLAG_PACKED_ACTIONS 4
 
 typedef unsigned long long crl_u64;

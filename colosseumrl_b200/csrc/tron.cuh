@@ -415,7 +415,9 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
         if (!(flags & 0x400)) tron_phase3(c, prm, o);
         tile.v[12][t] = tron_ctx_header(c);
         const uint2 rec = tron_pack_result(o);
-        if (flags & CRL_FLAG_COMPACT_RESULT) ((uint32_t *)result)[e0 + t] = rec.y;   // 4-byte record (see the header)
+        if (flags & CRL_FLAG_COMPACT2_RESULT)                                        // 2-byte record (see the header)
+            ((uint16_t *)result)[e0 + t] = (uint16_t)(((rec.y >> 8) & 0xfu) | (rec.y & 1u) << 4 | (rec.y >> 24) << 8);
+        else if (flags & CRL_FLAG_COMPACT_RESULT) ((uint32_t *)result)[e0 + t] = rec.y;   // 4-byte record
         else result[e0 + t] = rec;
     }
     tron_tile_store(tile, &maps, out, B, e0, n, false, true);

@@ -132,17 +132,21 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
                                             self.num_players, self.flags, self._stream))
         return new
 
-    def host_stepper(self, state: TronBatchState, stream=None, compact: bool = False, packed_actions: bool = False):
+    def host_stepper(self, state: TronBatchState, stream=None, compact=False, packed_actions: bool = False):
         """Graph-fused H2D actions -> step -> D2H result for host-side policies (see base.HostStepper).
         compact=True: the step writes the 4-byte record (CRL_FLAG_COMPACT_RESULT: terminal | alive | winners | ranking),
-        which halves the PCIe read-back; `decode_compact` rebuilds the reference's return values from it on the host.
+        which halves the PCIe read-back; compact=2: the 2-byte record (CRL_FLAG_COMPACT2_RESULT: alive | terminal << 4,
+        ranking), a quarter -- the read-back is the slowest leg of a host-side actor's step.  `decode_compact`
+        rebuilds the reference's return values from either on the host.
         packed_actions=True: the pinned action buffer is uint8 [B], 2 bits per player (`pack_actions`), a quarter of
         the PCIe upload.  NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
         from .base import HostStepper
         if not compact and not packed_actions:
             return HostStepper(self, state, (self.batch, 4), torch.int8, stream=stream)
-        rec = torch.empty((self.batch, 4 if compact else 8), dtype=torch.uint8, device=self.device)
-        flags = self.flags | (_lib.FLAG_COMPACT_RESULT if compact else 0) | (_lib.FLAG_PACKED_ACTIONS if packed_actions else 0)
+        width = 2 if compact == 2 else (4 if compact else 8)
+        rec = torch.empty((self.batch, width), dtype=torch.uint8, device=self.device)
+        flags = self.flags | {8: 0, 4: _lib.FLAG_COMPACT_RESULT, 2: _lib.FLAG_COMPACT2_RESULT}[width] | \
+            (_lib.FLAG_PACKED_ACTIONS if packed_actions else 0)
 
         def step(dev_actions):
             self._check(self._lib.crl_tron_step(state.packed.data_ptr(), state.packed.data_ptr(), dev_actions.data_ptr(),
@@ -167,7 +171,11 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         rewards = -2 * (deaths > 0) + 1, winners of a terminal step + 9 (TronGridEnvironment.py:313-320)."""
         import numpy as np
         rec = np.asarray(rec)
-        terminal, alive, winners, rk = rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3]
+        if rec.shape[1] == 2:                   # 2-byte record: winners of a terminal step = its alive players (:316-319)
+            alive, terminal, rk = rec[:, 0] & 15, (rec[:, 0] >> 4) & 1, rec[:, 1]
+            winners = alive * terminal
+        else:
+            terminal, alive, winners, rk = rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3]
         p = np.arange(self.num_players, dtype=np.uint8)[None, :]
         a = (alive[:, None] >> p) & 1
         w = ((winners[:, None] >> p) & 1) * (terminal[:, None] & 1)

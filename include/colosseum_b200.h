@@ -35,6 +35,7 @@ extern "C" {
 
 #define CRL_FLAG_AUTO_RESET 1 /* an environment whose stored terminal flag is set is replaced by new_state() before the step */
 #define CRL_FLAG_COMPACT_RESULT 2 /* crl_tron_step only: write the 4-byte record (below) instead of the 8-byte one */
+#define CRL_FLAG_COMPACT2_RESULT 8 /* crl_tron_step only: write the 2-byte record (below) */
 #define CRL_FLAG_PACKED_ACTIONS 4 /* crl_tron_step only: actions are uint8[B], 2 bits per player (action & 3) */
 
 /* statistics buffer: int64[CRL_STAT_ROWS][CRL_NSTAT] on the device, accumulated (+=) by step / rollout kernels.
@@ -76,7 +77,10 @@ int crl_philox_words(uint32_t *out, uint64_t seed, uint64_t first_env, uint32_t 
  *          With CRL_FLAG_COMPACT_RESULT: 4 bytes per environment = the second half of that record (terminal | alive |
  *          winners | ranking).  The rewards follow from it exactly as the reference computes them
  *          (TronGridEnvironment.py:313-320): reward[p] = alive[p] ? 1 : -1, plus 9 for the winners of a terminal step.
- *          It halves what a host-side actor has to read back over PCIe per step.                  */
+ *          It halves what a host-side actor has to read back over PCIe per step.
+ *          With CRL_FLAG_COMPACT2_RESULT: 2 bytes per environment, byte 0 = alive mask | terminal << 4, byte 1 =
+ *          ranking.  Nothing is lost: the winners of a terminal step ARE its alive players (:316-319) and the rewards
+ *          follow as above; the device -> host read of a host-side actor (the slowest leg of its step) halves again. */
 int64_t crl_tron_state_bytes(int N, int P, int64_t B);
 /* HOST function. generate_start_positions (TronGridEnvironment.py:183-226) with new_state's defaults:
  * heads[p] = y*N + x, directions[p] in {0 N, 1 E, 2 S, 3 W}. */

@@ -146,15 +146,16 @@ def test_host_stepper_matches_next_state():
     assert (sc.packed == sr.packed).all()
 
 
-def test_compact_host_stepper():
-    """host_stepper(compact=True): 4-byte records whose decode equals next_state's return values."""
+@pytest.mark.parametrize("compact", [True, 2])
+def test_compact_host_stepper(compact):
+    """host_stepper(compact=True / 2): 4- / 2-byte records whose decode equals next_state's return values."""
     from colosseumrl_b200.tron import BatchedTronGridEnvironment
     B = 513
     a_env = BatchedTronGridEnvironment("", batch=B, seed=4, auto_reset=True)
     b_env = BatchedTronGridEnvironment("", batch=B, seed=4, auto_reset=True)
     sa, _ = a_env.new_state()
     sb, _ = b_env.new_state()
-    stepper = b_env.host_stepper(sb, compact=True, packed_actions=True)   # warm-up applies one all-forward step
+    stepper = b_env.host_stepper(sb, compact=compact, packed_actions=True)   # warm-up applies one all-forward step
     sa, *_ = a_env.next_state(sa, None, torch.zeros((B, 4), dtype=torch.int8))
     rng = np.random.RandomState(1)
     terminals = 0
@@ -163,7 +164,7 @@ def test_compact_host_stepper():
         sa, pa, ra, ta, wa = a_env.next_state(sa, None, torch.from_numpy(a))
         stepper.actions_np[...] = b_env.pack_actions(a)
         rec = stepper()
-        assert rec.shape == (B, 4) and stepper.actions_np.shape == (B,)
+        assert rec.shape == (B, 2 if compact == 2 else 4) and stepper.actions_np.shape == (B,)
         alive, rewards, terminal, winners, ranking = b_env.decode_compact(rec)
         assert (alive == pa.cpu().numpy()).all() and (rewards == ra.cpu().numpy()).all()
         assert (terminal == ta.cpu().numpy()).all() and (winners == wa.cpu().numpy()).all()

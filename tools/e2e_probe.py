@@ -27,6 +27,8 @@ def run(name, make):
     print("%-34s %.2f us/step  %.2f G env-steps/s" % (name, dt / K * 1e6, B * K / dt / 1e9))
 
 
+run("packed actions + 2-byte record", lambda e, s, st: e.host_stepper(s, stream=st, compact=2, packed_actions=True))
+run("packed actions + 4-byte record", lambda e, s, st: e.host_stepper(s, stream=st, compact=True, packed_actions=True))
 run("H2D + step + D2H (compact)", lambda e, s, st: e.host_stepper(s, stream=st, compact=True))
 run("H2D + step + D2H (full record)", lambda e, s, st: e.host_stepper(s, stream=st))
 
