@@ -35,8 +35,8 @@ def build(force=False, verbose=False):
         sys.stderr.write(proc.stdout)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed (exit %d)" % proc.returncode)
-    with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as f:
-        f.write(proc.stdout)
+    with open(os.path.join(HERE, "csrc", "ptxas_info.txt"), "w") as f:     # registers / shared memory per kernel
+        f.write("".join(l for l in proc.stdout.splitlines(True) if "Compile time" not in l))
     return LIB
 
 
