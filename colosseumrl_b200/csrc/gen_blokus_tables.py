@@ -166,13 +166,14 @@ def emit(path):
     L.append("// 0..%d; the pentomino shapes are processed in groups of whole pieces that share slots %d.. :" % (n_le4 - 1, n_le4))
     L.append("#define BLK_FROWS %d" % FROWS)
     L.append("#define BLK_NSHAPE_LE4 %d" % n_le4)
-    # greedy grouping of the pentomino pieces, at most 24 shapes per group
+    # greedy grouping of the pentomino pieces, at most GROUP_CAP shapes per group
+    GROUP_CAP = int(os.environ.get("BLK_GROUP_CAP", "24"))
     groups, cur = [], None
     for pc in range(len(PIECES)):
         if len(PIECES[pc][1]) < 5:
             continue
         nsh = piece_shape0[pc + 1] - piece_shape0[pc]
-        if cur is None or cur[3] + nsh > 24:
+        if cur is None or cur[3] + nsh > GROUP_CAP:
             cur = [pc, pc + 1, piece_shape0[pc], nsh]
             groups.append(cur)
         else:
