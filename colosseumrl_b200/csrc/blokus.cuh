@@ -332,8 +332,19 @@ __device__ __forceinline__ int blk_enumerate(BlkSmem &sm, int c, int round, uint
     blk_tree_level(sm, ne, inv, 3, lane);
     blk_tree_level(sm, ne, inv, 4, lane);
     int base = 0;
+    uint32_t small = inv & ((1u << BLK_GROUP_P0[0]) - 1u);                                   // pieces of <= 4 cells
+    if ((small & 1u) && round != 0) {
+        // the monomino needs no test after round 0: every anchor is an allowed cell (ANC = A & D4), so it fits on each
+        // in all 8 orientations (k = 0) -- ids (y * 20 + x) * 40 + 5 o in anchor order, written 32 at a time
+        for (int i = lane; i < 8 * na; i += 32) {
+            const uint32_t w = sm.anch[i >> 3];
+            if (i < cap) st_global_u32(out + i, (int)(w >> 9) * 200 + (int)(w & 31u) * 40 + 5 * (i & 7));
+        }
+        base = 8 * na;
+        small &= ~1u;
+    }
 #pragma unroll 1
-    for (uint32_t rest = inv & ((1u << BLK_GROUP_P0[0]) - 1u); rest; rest &= rest - 1u)      // pieces of <= 4 cells
+    for (uint32_t rest = small; rest; rest &= rest - 1u)
         base = blk_emit_piece<false>(sm, ne, __ffs((int)rest) - 1, na, lane, base, out, cap);
 #pragma unroll 1
     for (int g = 0; g < BLK_NGROUP; g++) {                                                   // pentominoes, group by group
