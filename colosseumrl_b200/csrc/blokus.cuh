@@ -175,6 +175,33 @@ __device__ __forceinline__ uint32_t blk_tree_pass(BlkSmem &sm, int s0, int s1, u
     return m;
 }
 
+// ALL shapes of 2..4 cells (shapes 1..27: 2 dominoes, 6 trominoes, 19 tetrominoes) in ONE pass, straight from A:
+// FIT_s[q] = AND_i A[q + cell_i(s)] with the shape's own <= 4 cells (shorter shapes repeat cell 0).  As three tree
+// levels these 27 shapes cost three dependent passes that keep 2, 6 and 19 lanes busy (2 terms per row each); merged
+// they are one pass with four terms per row and 27 busy lanes.  (Measured: levels 2 + 3 merged -2.5 % of the step.)
+__device__ __forceinline__ uint32_t blk_tree_pass_le4(BlkSmem &sm, uint32_t ne, uint32_t inv, int lane) {
+    const uint4 t = BLK_SHAPE_TAB_G[1 + lane];                      // (the table is padded past the last shape)
+    const bool active = lane < BLK_NSHAPE_LE4 - 1 && (inv & t.y) != 0u && (ne & 1u) != 0u;
+    if (!__any_sync(0xffffffffu, active)) return 0u;
+    uint32_t acc = 0u;
+    if (active) {
+        const char *a0 = (const char *)sm.A + 4 * (t.z >> 3 & 7u), *a1 = (const char *)sm.A + 4 * (t.z >> 9 & 7u);
+        const char *a2 = (const char *)sm.A + 4 * (t.z >> 15 & 7u), *a3 = (const char *)sm.A + 4 * (t.z >> 21 & 7u);
+        const uint32_t x0 = t.z & 7u, x1 = t.z >> 6 & 7u, x2 = t.z >> 12 & 7u, x3 = t.z >> 18 & 7u;
+        char *po = (char *)sm.F + (t.w & 0xffffu);                  // own row 4
+#pragma unroll 5
+        for (int r = 0; r < 20; r++) {
+            const uint32_t f = (*(const uint32_t *)(a0 + 4 * r) >> x0) & (*(const uint32_t *)(a1 + 4 * r) >> x1) &
+                               (*(const uint32_t *)(a2 + 4 * r) >> x2) & (*(const uint32_t *)(a3 + 4 * r) >> x3) & 0xfffffff0u;
+            *(uint32_t *)(po + 4 * r) = f;
+            acc |= f;
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, acc != 0u);
+    __syncwarp();
+    return m << 1;
+}
+
 // the shapes with `level` (2..4) cells
 __device__ __forceinline__ void blk_tree_level(BlkSmem &sm, uint32_t &ne, uint32_t inv, int level, int lane) {
     const int s0 = BLK_LEVEL_S0[level - 1];
@@ -328,9 +355,7 @@ __device__ __forceinline__ int blk_enumerate(BlkSmem &sm, int c, int round, uint
     const int na = blk_allowed_and_anchors<true>(sm, c, round, lane);
     if (na == 0 || inv == 0u) return 0;
     uint32_t ne = blk_tree_root(sm, lane);
-    blk_tree_level(sm, ne, inv, 2, lane);
-    blk_tree_level(sm, ne, inv, 3, lane);
-    blk_tree_level(sm, ne, inv, 4, lane);
+    ne |= blk_tree_pass_le4(sm, ne, inv, lane);
     int base = 0;
     uint32_t small = inv & ((1u << BLK_GROUP_P0[0]) - 1u);                                   // pieces of <= 4 cells
     if ((small & 1u) && round != 0) {
