@@ -202,12 +202,6 @@ __device__ __forceinline__ uint32_t blk_tree_pass_le4(BlkSmem &sm, uint32_t ne, 
     return m << 1;
 }
 
-// the shapes with `level` (2..4) cells
-__device__ __forceinline__ void blk_tree_level(BlkSmem &sm, uint32_t &ne, uint32_t inv, int level, int lane) {
-    const int s0 = BLK_LEVEL_S0[level - 1];
-    ne |= blk_tree_pass(sm, s0, BLK_LEVEL_S0[level], ne, inv, lane) << s0;
-}
-
 // the shapes of pentomino group g into slots 28..; returns their non-empty flags (bit = shape - group start)
 __device__ __forceinline__ uint32_t blk_tree_group(BlkSmem &sm, int g, uint32_t ne, uint32_t inv, int lane) {
     __syncwarp();                // the previous group's readers are done with the shared slots
@@ -251,9 +245,9 @@ __device__ __forceinline__ int blk_any_move(BlkSmem &sm, int c, int round, uint3
     if (inv & 1u) return 1;                                  // the monomino fits on every anchor (ANC is a subset of A)
     if (!zeroed) { blk_zero_fit(sm, lane); zeroed = true; __syncwarp(); }  // (the common case never gets here)
     uint32_t ne = blk_tree_root(sm, lane);
+    ne |= blk_tree_pass_le4(sm, ne, inv, lane);              // (this is the negative path: the whole tree is needed anyway)
 #pragma unroll 1
     for (int level = 2; level <= 4; level++) {
-        blk_tree_level(sm, ne, inv, level, lane);
         const int s0 = BLK_LEVEL_S0[level - 1];
         if (blk_any_pass(sm, s0, BLK_LEVEL_S0[level], level, ne >> s0, inv, rows, lane)) return 1;
     }
