@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t blk_tree_pass(BlkSmem &sm, int s0, int s1, u
         const char *pa = (const char *)sm.A + (t.x >> 24);          // A row cy
         char *po = (char *)sm.F + (t.w & 0xffffu);                  // own row 4
         const uint32_t px = t.x >> 16, cx = t.x >> 20;              // wrap-mode shifts use the low 5 bits: px, cx <= 4
-#pragma unroll 5
+#pragma unroll 10
         for (int r = 0; r < 20; r++) {
             const uint32_t f = __funnelshift_r(*(const uint32_t *)(pp + 4 * r), 0u, px & 7u) &
                                __funnelshift_r(*(const uint32_t *)(pa + 4 * r), 0u, cx & 7u) & 0xfffffff0u;
@@ -189,7 +189,7 @@ __device__ __forceinline__ uint32_t blk_tree_pass_le4(BlkSmem &sm, uint32_t ne, 
         const char *a2 = (const char *)sm.A + 4 * (t.z >> 15 & 7u), *a3 = (const char *)sm.A + 4 * (t.z >> 21 & 7u);
         const uint32_t x0 = t.z & 7u, x1 = t.z >> 6 & 7u, x2 = t.z >> 12 & 7u, x3 = t.z >> 18 & 7u;
         char *po = (char *)sm.F + (t.w & 0xffffu);                  // own row 4
-#pragma unroll 5
+#pragma unroll 10
         for (int r = 0; r < 20; r++) {
             const uint32_t f = (*(const uint32_t *)(a0 + 4 * r) >> x0) & (*(const uint32_t *)(a1 + 4 * r) >> x1) &
                                (*(const uint32_t *)(a2 + 4 * r) >> x2) & (*(const uint32_t *)(a3 + 4 * r) >> x3) & 0xfffffff0u;
