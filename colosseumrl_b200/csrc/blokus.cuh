@@ -31,14 +31,15 @@
 // s = shape(piece, o).  The list is emitted in the reference's order piece -> anchor (row-major) -> o -> k, with
 // lanes = (anchor of a group of four, orientation), a SWAR popcount + one shuffle scan per 16 anchors (blk_emit_piece).
 //
-// FIT boards: the 91 oriented shapes are exactly the fixed polyominoes of 1..5 cells, so each is a smaller one plus
-// a cell and FIT_s[q] = FIT_parent[q + off] & A[q + c].  The tree is evaluated level by level with LANES = SHAPES:
-// each lane builds the 20 rows of its own shape's board (2 LDS, 2 shifts, 1 AND, 1 STS per row, parameters from a
-// per-shape table) and one ballot per pass yields the non-empty flags of up to 32 shapes: 3 passes for the shapes
-// of 2..4 cells, then one pass per group of pentomino pieces (the groups share the same slots; a group is built,
-// its pieces are emitted, the next group overwrites it).  Shapes whose pieces are not held or whose parent fits
-// nowhere are idle lanes; a pass without work is skipped.  Everything is a compact loop: the first version was
-// 86 KB of straight-line SASS and spent 70 % of its cycles waiting for the instruction cache.
+// FIT boards, LANES = SHAPES: the 91 oriented shapes are exactly the fixed polyominoes of 1..5 cells.  The 27 shapes
+// of 2..4 cells are built in ONE pass straight from A (blk_tree_pass_le4: lane l owns shape 1 + l and ANDs the <= 4
+// shifted A rows of its cells over the 20 rows: 4 LDS, 4 shifts, 2 LOP3, 1 STS per row); a pentomino is a tetromino
+// plus a cell, FIT_s[q] = FIT_parent[q + off] & A[q + c] (blk_tree_pass: 2 LDS, 2 shifts, 1 AND, 1 STS per row,
+// parameters from a per-shape table), one pass per group of pentomino pieces (the groups share the same slots; a
+// group is built, its pieces are emitted, the next group overwrites it).  One ballot per pass yields the non-empty
+// flags of up to 32 shapes.  Shapes whose pieces are not held or whose parent fits nowhere are idle lanes; a pass
+// without work is skipped.  Everything is a compact loop: the first version was 86 KB of straight-line SASS and
+// spent 70 % of its cycles waiting for the instruction cache.
 // The any-move test of the terminal check needs no anchor loop at all:
 // piece p has a move  <=>  OR_s OR_k (ANC & shift(FIT_s, cell_k)) != 0, again with lanes = shapes, level by level
 // with an early exit.
@@ -134,7 +135,7 @@ __device__ __forceinline__ int blk_allowed_and_anchors(BlkSmem &sm, int c, int r
     return total;
 }
 
-// ---- FIT boards through the polyomino tree, lanes = shapes ---------------------------------------------------
+// ---- FIT boards, lanes = shapes ---------------------------------------------------------------------------------
 // zero every board once per kernel (the passes only write rows 0..19 of the boards they build)
 __device__ __forceinline__ void blk_zero_fit(BlkSmem &sm, int lane) {
     uint4 *f4 = (uint4 *)sm.F;
