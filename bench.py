@@ -1,31 +1,38 @@
 #!/usr/bin/env python
-"""Benchmark of the batched game-dynamics hot path (BASELINE.json metric: batched env-steps/sec).
+"""Benchmark of the batched game-dynamics hot path (BASELINE.json metric: batched env-steps/sec, Tron & Blokus 4-player).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tron|ttt4|blokus] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload all|tron|blokus|ttt4|ttt2] [--impl b200|reference]
 
-One "step" = one next_state pass over ONE batch of environments of the workload's configured size
-(tron: 65,536 envs, the configuration BASELINE.json's metric is quoted on).  N > 1 is launched by torchrun: one
-rank per GPU, each owning a contiguous slice of global environment ids, no data-path collective, one NCCL
-all-reduce of the fused episode statistics per measurement window (weak scaling).
+ONE JSON line.  The top level is the headline workload (default: Tron 4-player 19x19, 65,536 batched envs --
+BASELINE.json configs[1], the configuration the metric is quoted on); with --workload all (the default) the other
+configurations of BASELINE.json ride along under "workloads": {"blokus": {...}, "ttt4": {...}, "ttt2": {...}}, each
+with its own value / ms_per_step / roofline / e2e / cpu_baseline.  One "step" = one next_state pass over ONE batch
+of environments of the workload's configured size (Blokus: valid_actions + pick + next_state).  N > 1 is launched
+by torchrun: one rank per GPU, each owning a contiguous slice of global environment ids, no data-path collective,
+one NCCL all-reduce of the fused episode statistics per measurement window (weak scaling).
 
 How it is timed
   * L2: the configured batch (13.6 MB of Tron state) would sit in the 126 MB L2, so every rank holds G independent
-    replicas of the batch (>= 4 x L2 of state in total) and consecutive steps cycle through them: each step's
-    state comes from and goes back to HBM ("inputs larger than L2").  No flush kernel is needed.
-  * value: the K timed steps are captured in ONE CUDA graph (the step is a few microseconds, Python launch
-    overhead would dominate) and replayed between two CUDA events on the launching stream; barrier +
-    synchronize on both sides; max over ranks.  ms_per_step = elapsed / K.
+    replicas of the batch (>= 4 x L2 of state in total) and consecutive steps cycle through them: each step's state
+    comes from and goes back to HBM ("inputs larger than L2").  No flush kernel is needed.
+  * value: a K-step pass is a few hundred microseconds at the driver's K = 20, far too short to time on its own, so
+    the timed region is R back-to-back repetitions of the K-step sequence ("reps", chosen so that the region lasts
+    >= --min-ms, default 50 ms), captured in ONE CUDA graph (Python launch overhead would dominate a 4 us step) and
+    replayed once between two CUDA events on the launching stream.  The statistics row-sum (crl_stats_reduce) and the
+    NCCL all-reduce of the 32-slot vector follow on the same stream INSIDE the timed region; barrier + synchronize on
+    both sides; max over ranks.  ms_per_step = elapsed / (K * R).
   * e2e: through the public Python API for host-side policies (env.host_stepper: one CUDA-graph launch = H2D copy
-    of the pinned actions + step kernel + D2H copy of the result record into pinned memory); the actor
-    double-buffers two environment batches (launch batch A's step, consume batch B's result record meanwhile), so
-    every step's H2D and D2H are inside the timed region and overlap only with the neighbouring batch's step.
-  * roofline: algorithmic bytes per env-step x envs per launch / mean launch duration
-    (elapsed / K, so launch gaps count against us) vs the measured copy bandwidth in MEASURED_PEAKS.json.
+    of the pinned actions + step kernel + D2H copy of the result record into pinned memory), 8 environment batches
+    in flight, K * Re steps (>= --min-ms as well) so that the pipeline's ramp and drain are < 1 % of the region.
+  * roofline: algorithmic bytes per env-step x envs per launch / mean launch duration vs the
+    measured copy bandwidth in MEASURED_PEAKS.json; Blokus additionally against the integer issue roof (warp
+    instructions per step from the committed ncu count, INT_PEAKS.json).
   * cpu_baseline / --impl reference: the CPU oracle port (oracle/liboracle.so: plain-C restatement of the
     reference's Python -- the reference itself is Python and cannot travel to the GPU box) on all host cores.
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -38,16 +45,25 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 L2_BYTES = 126 << 20
+POLICY = "philox4x32-10 uniform random, auto-reset"
 
 WORKLOADS = {
     # name: description, per-GPU batch, algorithmic bytes per env-step, state bytes per env
     "tron": dict(desc="Tron 4-player 19x19, 65,536 batched envs, random actions (BASELINE.json configs[1])",
-                 B=65536, bytes=424, state=208, kernel="tron_step_kernel", launches=1),
-    "ttt4": dict(desc="Tic Tac Toe 4-player 3x3x3, 1,048,576 batched envs, random self-play (BASELINE.json configs[3])",
-                 B=1 << 20, bytes=36, state=16, kernel="ttt_rollout_kernel", launches=1),
+                 B=65536, bytes=424, state=208, kernel="tron_step_warp_kernel", launches=1, dtype="u32"),
     "blokus": dict(desc="Blokus 4-player 20x20, valid_actions + next_state over 16,384 batched games (BASELINE.json configs[2])",
-                   B=16384, bytes=2196, state=352, kernel="blokus_legal_kernel", launches=3),
+                   B=16384, bytes=2196, state=352, kernel="blokus_legal_kernel", launches=3, dtype="u32"),
+    "ttt4": dict(desc="Tic Tac Toe 4-player 3x3x3, 1,048,576 batched envs, random self-play (BASELINE.json configs[3])",
+                 B=1 << 20, bytes=36, state=16, kernel="ttt_rollout_kernel", launches=1, dtype="u32"),
+    "ttt2": dict(desc="Tic Tac Toe 2-player 3x3, single env, random self-play through next_state (BASELINE.json configs[0])",
+                 B=1, bytes=36, state=16, kernel="ttt_step_kernel", launches=1, dtype="u32"),
 }
+ORDER = ["tron", "blokus", "ttt4", "ttt2"]
+
+
+def config_of(name, B):
+    """The `config` object -- identical in both arms (--impl b200 / reference) for the same workload."""
+    return {"workload": WORKLOADS[name]["desc"], "batch_per_gpu": B, "policy": POLICY}
 
 
 def peaks():
@@ -55,6 +71,16 @@ def peaks():
     if os.path.exists(path):
         return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _load_json(*parts):
+    path = os.path.join(ROOT, *parts)
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
 
 
 class ClockSampler:
@@ -85,7 +111,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.004)
 
     def start(self):
         if self.nv:
@@ -102,7 +128,7 @@ class ClockSampler:
 
 def graph_upload(graph, stream):
     """cudaGraphUpload of a captured torch graph: without it the first replay pays for moving the executable graph to
-    the device inside the timed region.  (No kernel runs here; the K timed steps are the graph's only execution.)"""
+    the device inside the timed region.  (No kernel runs here; the timed steps are the graph's only execution.)"""
     from colosseumrl_b200 import _cudart
     _cudart.check(_cudart.rt().cudaGraphUpload(graph.raw_cuda_graph_exec(), stream.cuda_stream), "cudaGraphUpload")
 
@@ -114,24 +140,29 @@ def _cpu_batch(workload, B):
         return orc.TronBatch(B, 19, 4)
     if workload == "ttt4":
         return orc.TTTBatch(B, 4)
+    if workload == "ttt2":
+        return orc.TTTBatch(B, 2)
     return orc.BlokusBatch(B)
 
 
-def cpu_baseline(workload, target_s=12.0):
+def cpu_baseline(workload, target_s=8.0):
     """Bounded sample of the same workload on all host cores (C oracle port; K steps per env kept in cache)."""
     from oracle import oracle as orc
     cores = orc.num_threads()
     B = WORKLOADS[workload]["B"]
     if workload == "blokus":
         B = 16 * cores                                   # bounded sample: the CPU needs ~2 ms per Blokus step
+    if workload == "ttt2":
+        cores = 1                                        # configs[0]: ONE environment, one core
     ob = _cpu_batch(workload, B)
     ob.rollout(0, 0, 0, 2, fresh=True, nthreads=cores)
+    n0 = 4 if workload != "ttt2" else 100000
     t0 = time.perf_counter()
-    ob.rollout(0, 0, 2, 4, nthreads=cores)
-    rate = B * 4 / (time.perf_counter() - t0)
+    ob.rollout(0, 0, 2, n0, nthreads=cores)
+    rate = B * n0 / (time.perf_counter() - t0)
     K = max(4, int(rate * target_s / B))
     t0 = time.perf_counter()
-    ob.rollout(0, 0, 6, K, nthreads=cores)
+    ob.rollout(0, 0, 2 + n0, K, nthreads=cores)
     dt = time.perf_counter() - t0
     return {"value": B * K / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
             "sample": "%d envs x %d steps (%.1f s) of the C oracle port of the reference's Python, %d pthreads" % (B, K, dt, cores)}
@@ -170,38 +201,50 @@ def _reference_cython_core(seconds=2.0):
         return {"unavailable": repr(e)}
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port, all host threads), same config / metric / step."""
-    if int(os.environ.get("RANK", "0")) != 0:
-        return
+def reference_workload(name, K, W, n_gpus):
+    """One workload of the reference arm: the reference's CPU path (oracle port, all host threads), same config /
+    metric / step as the GPU arm: one step = one next_state pass over the whole configured batch."""
     from oracle import oracle as orc
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS[name]
     B = wl["B"]
-    cores = orc.num_threads()
-    ob = _cpu_batch(args.workload, B)
+    cores = 1 if name == "ttt2" else orc.num_threads()
+    per = 1 if name != "ttt2" else 1000           # configs[0] is ONE environment: a "step" of 1 env is ~50 ns of C, so
+    ob = _cpu_batch(name, B)                       # every timed step is repeated `per` times (reported as reps)
     ob.rollout(0, 0, 0, 1, fresh=True, nthreads=cores)
     t = 1
-    for _ in range(args.warmup):
-        ob.rollout(0, 0, t, 1, nthreads=cores); t += 1
+    for _ in range(W):
+        ob.rollout(0, 0, t, per, nthreads=cores); t += per
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ob.rollout(0, 0, t, 1, nthreads=cores); t += 1
+    for _ in range(K):
+        ob.rollout(0, 0, t, per, nthreads=cores); t += per
     dt = time.perf_counter() - t0
-    value = B * args.steps / dt
+    value = B * K * per / dt
     line = {"impl": "reference", "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "n_gpus": n_gpus, "steps": K, "warmup": W, "reps": per, "ms_per_step": dt / (K * per) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "batch_per_step": B, "policy": "philox4x32-10 uniform random, auto-reset",
-                       "note": "the reference is Python + Cython and cannot travel to the GPU box; this arm times its "
-                               "plain-C restatement (oracle/liboracle.so, reference int64 layout) on all host cores -- "
+            "config": config_of(name, B),
+            "method": {"note": "the reference is Python + Cython and cannot travel to the GPU box; this arm times its "
+                               "plain-C restatement (oracle/liboracle.so, reference int64 layout) on the host cores -- "
                                "one step = one next_state pass over the whole batch, as on the GPU arm"},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                             "sample": "%d envs x %d steps" % (B, args.steps)},
+                             "sample": "%d envs x %d steps" % (B, K * per)},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if args.workload == "tron":
+    if name == "tron":
         core = _reference_cython_core()
         if core is not None:
             line["reference_cython_core"] = core
+    return line
+
+
+def run_reference(args):
+    """--impl reference: rank 0 alone runs and prints; the other ranks exit 0 without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    names = ORDER if args.workload == "all" else [args.workload]
+    lines = [reference_workload(n, args.steps, args.warmup, args.gpus) for n in names]
+    line = lines[0]
+    if len(lines) > 1:
+        line["workloads"] = {n: l for n, l in zip(names[1:], lines[1:])}
     print(json.dumps(line), file=REAL_STDOUT, flush=True)
 
 
@@ -239,10 +282,10 @@ def _pipelined_e2e_drain(work):
 
 
 class TronWL:
-    def __init__(self, dev, rank, B, G, K):
+    def __init__(self, dev, rank, B, G):
         import torch
         from colosseumrl_b200.tron import BatchedTronGridEnvironment
-        self.torch, self.B, self.G = torch, B, G
+        self.torch, self.B, self.G, self.dev = torch, B, G, dev
         # one env object per replica: replica g of rank r owns global env ids [(r*G + g)*B, +B)
         self.envs = [BatchedTronGridEnvironment("", batch=B, device=dev, seed=0, auto_reset=True,
                                                 first_env_id=(rank * G + g) * B) for g in range(G)]
@@ -250,7 +293,7 @@ class TronWL:
         for e in self.envs[1:]:
             e.stats_rows = self.envs[0].stats_rows                      # one statistics vector per rank
         self.local_t = [0] * G
-        self.actions = torch.empty((K, B, 4), dtype=torch.int8, device=dev)   # resident inputs of the timed steps
+        self.actions = None                                            # resident inputs of the timed steps
         # e2e: the host policy hands over packed actions (uint8 per env, 2 bits per player) and reads the 2-byte record
         self.h_actions = [torch.from_numpy(BatchedTronGridEnvironment.pack_actions(
             np.random.RandomState(rank + i).randint(-1, 2, size=(B, 4)).astype(np.int8))).pin_memory() for i in range(2)]
@@ -258,10 +301,13 @@ class TronWL:
         self.stepper_kwargs = {"compact": 2, "packed_actions": True}
         self.steppers = None
 
-    def prepare(self, k0, K):
-        """Pre-generate the actions of timed steps k0..k0+K-1 (Philox policy kernel), outside the timed region."""
+    def prepare(self, k0, n):
+        """Pre-generate the actions of timed steps k0..k0+n-1 (Philox policy kernel), outside the timed region."""
+        if self.actions is None or self.actions.shape[0] < n:
+            self.actions = None
+            self.actions = self.torch.empty((n, self.B, 4), dtype=self.torch.int8, device=self.dev)
         lt = list(self.local_t)
-        for k in range(K):
+        for k in range(n):
             g = (k0 + k) % self.G
             self.envs[g].random_actions(lt[g], out=self.actions[k])
             lt[g] += 1
@@ -288,7 +334,7 @@ class TronWL:
 
 
 class TTTWL:
-    def __init__(self, dev, rank, B, G, K):
+    def __init__(self, dev, rank, B, G):
         import torch
         from colosseumrl_b200.tictactoe import BatchedTicTacToe4PlayerEnv
         self.torch, self.B, self.G = torch, B, G
@@ -303,7 +349,7 @@ class TTTWL:
         self.h2d, self.d2h = B, B * 4
         self.steppers = None
 
-    def prepare(self, k0, K):
+    def prepare(self, k0, n):
         pass
 
     def step(self, k, slot=None):
@@ -323,7 +369,7 @@ class TTTWL:
 
 
 class BlokusWL:
-    def __init__(self, dev, rank, B, G, K):
+    def __init__(self, dev, rank, B, G):
         import torch
         from colosseumrl_b200.blokus import BatchedBlokusEnvironment
         self.torch, self.B, self.G = torch, B, G
@@ -337,11 +383,9 @@ class BlokusWL:
                       for _ in range(G)]
         self.act = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(G)]
         self.h_actions = torch.full((B,), -1, dtype=torch.int32).pin_memory()
-        self.h_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
-        self.h_result = torch.empty((B, 8), dtype=torch.uint8).pin_memory()
         self.h2d, self.d2h = B * 4, B * 8 + B * 4
 
-    def prepare(self, k0, K):
+    def prepare(self, k0, n):
         pass
 
     def step(self, k, slot=None):
@@ -423,33 +467,76 @@ class BlokusWL:
         return self.envs[0]
 
 
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """torch / torch.distributed handles and rank geometry of this process."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    wl = WORKLOADS[args.workload]
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+
+def issue_roofline(args, stats, launch_ms_step, clk):
+    """Blokus against the integer ISSUE roof: warp instructions per env-step (committed ncu count of this very
+    workload, profiles/blokus_inst.json) x env-steps/s  vs  4 warp-instructions / clk / SM (INT_PEAKS.json)."""
+    inst = _load_json("profiles", "blokus_inst.json")
+    ip = _load_json("INT_PEAKS.json")
+    if not inst or not ip or not inst.get("warp_inst_per_env_step"):
+        return None
+    B = WORKLOADS["blokus"]["B"]
+    per_step = float(inst["warp_inst_per_env_step"])
+    achieved = per_step * B / (launch_ms_step * 1e-3) / 1e12
+    mhz = float((clk or {}).get("sm_mhz") or ip.get("sm_mhz", 1965.0))
+    peak = 4.0 * ip.get("sms", 148) * mhz * 1e6 / 1e12
+    mix = ip.get("mix_warp_inst_per_clk_per_sm")
+    out = {"bound": "int_issue", "achieved": achieved, "peak": peak, "unit": "T warp-inst/s", "frac": achieved / peak,
+           "warp_inst_per_env_step": per_step, "count_source": inst.get("source"),
+           "peak_source": "4 warp-inst / clk / SM x %d SMs x %.0f MHz (sampled SM clock of this run; INT_PEAKS.json)" % (ip.get("sms", 148), mhz)}
+    if mix:
+        mix_peak = float(mix) * ip.get("sms", 148) * mhz * 1e6 / 1e12
+        out["frac_of_measured_int_mix_peak"] = achieved / mix_peak
+        out["measured_int_mix_peak"] = mix_peak
+    return out
+
+
+def measure_b200(name, args, cx, with_cpu):
+    """Times one workload on this rank's GPU; rank 0 returns the workload's result object, the others None."""
+    torch = cx.torch
+    dev, rank, world = cx.dev, cx.rank, cx.world
+    wl = WORKLOADS[name]
     B, K, W = (args.batch or wl["B"]), args.steps, args.warmup
     if args.scaling == "strong":                     # total work fixed: the configured batch is split over the ranks
         assert B % world == 0, "--scaling strong: the batch must divide by the number of GPUs"
         B //= world
-    per_replica = wl["state"] * B if args.workload != "blokus" else (wl["state"] + 435 * 4) * B
+    per_replica = wl["state"] * B if name != "blokus" else (wl["state"] + 435 * 4) * B
     G = args.replicas or max(2, -(-4 * L2_BYTES // per_replica))       # >= 4 x L2 of state per cycle
-    work = {"tron": TronWL, "ttt4": TTTWL, "blokus": BlokusWL}[args.workload](dev, rank, B, G, K)
+    work = {"tron": TronWL, "ttt4": TTTWL, "blokus": BlokusWL}[name](dev, rank, B, G)
     stream = torch.cuda.current_stream(dev)
     if args.no_stats:
         for e in work.envs:
             e.collect_stats = False
 
-    # warm-up (eager launches through the public API), then capture the K timed steps in one CUDA graph
+    # warm-up: W eager launches through the public API as requested, plus enough to touch every replica once
     k = 0
-    for _ in range(max(W, G)):
+    extra_warm = max(0, G - W)
+    for _ in range(W + extra_warm):
         work.step(k); k += 1
     torch.cuda.synchronize()
     S = max(1, min(args.streams, G))
@@ -482,28 +569,38 @@ def run_b200(args):
         torch.cuda.synchronize()
         return gr
 
-    # for the report only (untimed as far as the contract goes, it doubles as warm-up): the same steps as ONE dependent
-    # chain, i.e. every launch waits for its predecessor
-    serial, Ks = None, 0
-    if S > 1:
-        Ks = min(K, 400)
-        gs = capture(k, Ks, 1)
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        gs.replay()
-        s1.record(stream)
+    def timed_replay(gr):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        gr.replay()
+        b.record(stream)
         torch.cuda.synchronize()
-        serial = s0.elapsed_time(s1) / Ks
-        k += Ks
+        return a.elapsed_time(b)
+
+    # size the timed region: a first K-step graph (one chain) gives the step time; R repetitions of the K-step sequence
+    # then fill >= --min-ms.  (These K steps are real steps of the same sequence: they double as warm-up.)
+    g0 = capture(k, K, 1)
+    (est,) = cx.max_over_ranks([max(timed_replay(g0) / K, 1e-4)])      # every rank must derive the same R
+    k += K
+    del g0
+    node_cap = 30000 // wl["launches"]
+    R = max(1, min(int(math.ceil(args.min_ms / (K * est))), max(1, node_cap // K)))
+    # for the report only: the same steps as ONE dependent chain (every launch waits for its predecessor)
+    serial, Rs = None, 0
+    if S > 1:
+        Rs = max(1, min(R // 2, max(1, node_cap // K)))
+        gs = capture(k, K * Rs, 1)
+        serial = timed_replay(gs) / (K * Rs)
+        k += K * Rs
         del gs
-    graph = capture(k, K, S)
+    n_timed = K * R
+    graph = capture(k, n_timed, S)
     work.stats_env.stats_rows.zero_()              # count the timed steps only
+    total_stats, _ = work.stats_env.all_reduce_stats(async_op=True)    # warm-up: NCCL communicator setup (zeros)
     torch.cuda.synchronize()
 
-    clocks = ClockSampler(local)
-    if world > 1:
-        work.stats_env.all_reduce_stats()          # warm-up: NCCL communicator setup happens on the first collective
-        dist.barrier()
+    clocks = ClockSampler(cx.local)
+    cx.barrier()
     torch.cuda.synchronize()
     clocks.start()
     ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -511,90 +608,170 @@ def run_b200(args):
     ev0.record(stream)
     graph.replay()
     ev1.record(stream)
-    total_stats = work.stats_env.all_reduce_stats()                   # the only collective: 256 B, once per window
+    # the only collective: own row-sum kernel (256 rows -> 32 slots) + one all-reduce of 256 B, stream-ordered behind
+    # the steps and inside the timed region; the host does not block on it
+    total_stats, work_h = work.stats_env.all_reduce_stats(async_op=True)
+    if work_h is not None:
+        work_h.wait()
     ev2.record(stream)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    cx.barrier()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
-    k += K
+    k += n_timed
     steps_ms = ev0.elapsed_time(ev1)
-    dev_ms = steps_ms + (ev1.elapsed_time(ev2) if world > 1 else 0.0)
-    tmax = torch.tensor([dev_ms, steps_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_ms_max, steps_ms_max = float(tmax[0].item()), float(tmax[1].item())
-    ms_per_step = dev_ms_max / K
-    value = world * B * K / (dev_ms_max * 1e-3)
-    launch_ms = steps_ms_max / K / wl["launches"]
+    dev_ms = ev0.elapsed_time(ev2)
+    dev_ms_max, steps_ms_max = cx.max_over_ranks([dev_ms, steps_ms])
+    ms_per_step = dev_ms_max / n_timed
+    value = world * B * n_timed / (dev_ms_max * 1e-3)
+    step_ms = steps_ms_max / n_timed
+    launch_ms = step_ms / wl["launches"]
 
-    # ---- end to end through the public API with host buffers
-    Ke = min(K, 1000)      # long enough that the 8-deep pipeline's ramp and drain are < 1 % of the timed region
+    # ---- end to end through the public API with host buffers: K x Re steps (>= --min-ms)
     for j in range(3):
         work.e2e_step(k); k += 1
     work.e2e_drain()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    dbg = [] if os.environ.get("CRL_E2E_DEBUG") else None
-    for j in range(Ke):
-        t_ = time.perf_counter()
+    probe_n = min(64, K)
+    t_ = time.perf_counter()
+    for j in range(probe_n):
         work.e2e_step(k); k += 1
-        if dbg is not None:
-            dbg.append(time.perf_counter() - t_)
     work.e2e_drain()
-    if dbg:
-        sys.stderr.write("e2e per-call ms: " + " ".join("%.2f" % (x * 1e3) for x in dbg) + "\n")
+    (est_e,) = cx.max_over_ranks([max((time.perf_counter() - t_) / probe_n * 1e3, 1e-3)])
+    Re = max(1, int(math.ceil(args.min_ms / (K * est_e))))
+    Ke = K * Re
+    torch.cuda.synchronize()
+    cx.barrier()
+    e0.record(stream)
+    for j in range(Ke):
+        work.e2e_step(k); k += 1
+    work.e2e_drain()
     e1.record(stream)
     torch.cuda.synchronize()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * Ke / (float(e2e_ms.item()) * 1e-3)
+    (e2e_ms,) = cx.max_over_ranks([e0.elapsed_time(e1)])
+    e2e_value = world * B * Ke / (e2e_ms * 1e-3)
     clk = clocks.stop()
 
+    out = None
     if rank == 0:
         peak, peak_src = peaks()
         stats = total_stats.cpu().numpy()
         bytes_per_step = wl["bytes"]
-        if args.workload == "blokus" and stats[0] > 0:
+        if name == "blokus" and stats[0] > 0:
             # 352 in + 352 out + 4 action + 8 result + 4 count + 4 per listed id (actual mean list length of this run)
             bytes_per_step = 720 + 4 * float(stats[13]) / float(stats[0])
-        achieved = bytes_per_step * B / (steps_ms_max / K * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        line = {
+        achieved = bytes_per_step * B / (step_ms * 1e-3) / 1e9
+        traffic = (_load_json("profiles", "traffic_%s.json" % name) or {}).get("dram_bytes_per_launch")
+        hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+               "traffic": traffic, "peak_source": peak_src, "kernel": wl["kernel"],
+               "algorithmic_bytes_per_env_step": bytes_per_step, "launch_ms": launch_ms,
+               "note": "achieved = algorithmic bytes of the timed steps / device time of the steps (events around the graph)",
+               "single_chain": None if serial is None else
+               {"ms_per_step": serial, "frac": bytes_per_step * B / (serial * 1e-3) / 1e9 / peak,
+                "note": "same steps as one dependent chain (every launch waits for its predecessor, PDL only)"}}
+        roofline = hbm
+        if name == "blokus":
+            issue = issue_roofline(args, stats, step_ms, clk)
+            if issue is not None:
+                issue.update(kernel=wl["kernel"], launch_ms=launch_ms, traffic=traffic, hbm=hbm,
+                             note="integer issue binds this path (SURVEY 8d); the HBM figure is kept as `hbm`")
+                roofline = issue
+        out = {
             "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": max(W, G) + (Ks if serial is not None else 0), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": "u64" if args.workload == "tron" else "u32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "batch_per_gpu": B, "policy": "philox4x32-10 uniform random, auto-reset",
-                       "l2": "inputs larger than L2: %d independent replicas of the batch per GPU (%.0f MB of state) "
+            "warmup": W, "reps": R, "timed_steps": n_timed, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+            "config": config_of(name, B),
+            "method": {"l2": "inputs larger than L2: %d independent replicas of the batch per GPU (%.0f MB of state) "
                              "stepped round-robin, no flush kernel" % (G, G * per_replica / 1e6),
-                       "launch": "K steps captured in one CUDA graph" + ("" if S == 1 else ", the independent replicas spread over %d parallel chains (a replica's own steps stay ordered)" % S),
-                       "chains": S, "state_bytes_per_env": wl["state"],
-                       "parallelism": "env-sharded x%d, no data-path collective, 1 stats all-reduce" % world},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": wl["kernel"],
-                         "algorithmic_bytes_per_env_step": bytes_per_step, "launch_ms": launch_ms,
-                         "note": "achieved = algorithmic bytes of the K timed steps / device time of the timed region",
-                         "single_chain": None if serial is None else
-                         {"ms_per_step": serial, "frac": bytes_per_step * B / (serial * 1e-3) / 1e9 / peak,
-                          "note": "same steps as one dependent chain (every launch waits for its predecessor)"}},
+                       "launch": "R = %d repetitions of the K-step sequence captured in one CUDA graph" % R +
+                                 ("" if S == 1 else ", the independent replicas spread over %d parallel chains (a replica's own steps stay ordered)" % S),
+                       "chains": S, "state_bytes_per_env": wl["state"], "warmup_extra_steps": extra_warm + K + K * Rs,
+                       "timed_region_ms": dev_ms_max, "steps_ms": steps_ms_max,
+                       "stats_allreduce_ms": dev_ms_max - steps_ms_max,
+                       "parallelism": "env-sharded x%d, no data-path collective, 1 stats all-reduce inside the timed region" % world},
+            "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": work.h2d,
                     "d2h_bytes_per_step": work.d2h, "steps": Ke},
-            "gpu_launches": K * wl["launches"] * world,
+            "gpu_launches": n_timed * wl["launches"] * world + world,
             "clocks": clk,
             "wall_s_timed_region": wall,
             "episodes": int(stats[1]), "env_steps_counted": int(stats[0]),
         }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(args.workload)
+        if with_cpu:
+            out["cpu_baseline"] = cpu_baseline(name)
+    # release this workload's device memory before the next one
+    del graph, work
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_ttt2(args, cx):
+    """configs[0]: ONE Tic Tac Toe 2-player environment stepped through the reference's call shapes (string actions,
+    functional next_state) on the single-environment adapter -- every call is a pack + kernel + unpack round trip, so
+    this is the engine's launch-latency floor, not a throughput figure; the batched classes are the product."""
+    torch = cx.torch
+    from colosseumrl_b200.single import TicTacToe2PlayerEnv
+    import random
+    env = TicTacToe2PlayerEnv("", device=cx.dev)
+    rng = random.Random(0)
+
+    def play(n):
+        done, state, players = 0, None, None
+        while done < n:
+            if state is None:
+                state, players = env.new_state()
+            p = players[0]
+            a = rng.choice(env.valid_actions(state, p))
+            state, players, _, terminal, _ = env.next_state(state, players, [a])
+            done += 1
+            if terminal:
+                state = None
+        return done
+
+    play(max(3, args.warmup))
+    torch.cuda.synchronize()
+    n = max(args.steps, 200)
+    t0 = time.perf_counter()
+    play(n)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if cx.rank != 0:
+        return None
+    v = n / dt
+    return {"metric": "batched env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "reps": 1, "timed_steps": n, "ms_per_step": dt / n * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config_of("ttt2", 1),
+            "method": {"note": "single-environment string-action adapter (colosseumrl_b200.single): valid_actions + "
+                               "next_state per step, each a host round trip; wall-clock timed (launch-latency-bound)"},
+            "roofline": None,
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 9 + 2, "d2h_bytes_per_step": 9 + 2 + 4,
+                    "steps": n},
+            "gpu_launches": 4 * n,
+            "cpu_baseline": cpu_baseline("ttt2", target_s=2.0) if cx.world == 1 and not args.no_cpu else None}
+
+
+def run_b200(args):
+    cx = Ctx()
+    names = ORDER if args.workload == "all" else [args.workload]
+    if cx.world > 1 or args.scaling == "strong" or args.batch:
+        names = [n for n in names if n != "ttt2"] or names      # the single-env case has nothing to shard
+    results = []
+    for n in names:
+        with_cpu = cx.world == 1 and not args.no_cpu
+        if n == "ttt2":
+            results.append(measure_ttt2(args, cx))
+        else:
+            results.append(measure_b200(n, args, cx, with_cpu))
+    if cx.rank == 0:
+        line = results[0]
+        if len(results) > 1:
+            line["workloads"] = {n: r for n, r in zip(names[1:], results[1:])}
         print(json.dumps(line), file=REAL_STDOUT, flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.destroy_process_group()
 
 
 REAL_STDOUT = sys.stdout
@@ -614,10 +791,13 @@ def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--workload", default="tron", choices=sorted(WORKLOADS))
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="all", choices=["all"] + ORDER,
+                    help="all (default): Tron is the headline line, the other BASELINE.json configurations are nested under `workloads`")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--min-ms", type=float, default=50.0,
+                    help="minimum length of every timed region; the K-step sequence is repeated to fill it")
     ap.add_argument("--replicas", type=int, default=0, help="independent batch replicas per GPU (0 = enough for 4 x L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stats", action="store_true", help="exploration: skip the fused episode statistics")

@@ -25,11 +25,15 @@ SIGNATURES = {
     "crl_last_error": (C.c_char_p, []),
     "crl_init": (_int, [_int]),
     "crl_philox_words": (_int, [_vp, _u64, _u64, _u32, _u32, _i64, _vp]),
+    "crl_stats_reduce": (_int, [_vp, _vp, _int, _vp]),
     "crl_tron_state_bytes": (_i64, [_int, _int, _i64]),
     "crl_tron_start_positions": (_int, [_int, _int, C.POINTER(_i32), C.POINTER(_i32)]),
     "crl_tron_reset": (_int, [_vp, _vp, _i64, _int, _int, _vp]),
     "crl_tron_start_positions_at": (_int, [_int, _int, _int, _int, C.POINTER(_i32), C.POINTER(_i32)]),
     "crl_tron_reset_at": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp]),
+    "crl_tron_start_positions_spawns": (_int, [_int, _int, _int, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "crl_tron_reset_spawns": (_int, [_vp, _vp, _i64, _int, _int, _int, C.POINTER(_i32), _vp]),
+    "crl_tron_step_spawns": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, C.POINTER(_i32), _vp]),
     "crl_tron_step": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
     "crl_tron_policy_random": (_int, [_vp, _u64, _u64, _u32, _i64, _vp]),
     "crl_tron_rollout": (_int, [_vp, _vp, _vp, _u64, _u64, _u32, _int, _i64, _int, _int, _vp]),

@@ -46,6 +46,10 @@ class HostStepper:
         """step(dev_actions) -> device tensor holding the step's result record; default: env.step_ in place on
         `state`, the full record.  (Tron passes a compact-record step: half the bytes to read back.)"""
         self.env, self.state, self.stream = env, state, stream
+        with torch.cuda.device(env.device):
+            self._build(env, state, action_shape, action_dtype, stream, step)
+
+    def _build(self, env, state, action_shape, action_dtype, stream, step):
         self.actions = torch.zeros(action_shape, dtype=action_dtype).pin_memory()
         self._dev_actions = torch.zeros(action_shape, dtype=action_dtype, device=env.device)
         if step is None:
@@ -99,6 +103,26 @@ class HostStepper:
         return self.wait()
 
 
+class _DeviceBoundLib:
+    """The C ABI takes no device argument: a launch goes to the CUDA context that is current on the calling thread.
+    Every call made through this proxy runs with the environment's device current (and restores the caller's), so
+    environments on different GPUs can live in one process and the user's `torch.cuda.current_device()` never moves."""
+
+    def __init__(self, lib, index):
+        self._lib, self._index = lib, index
+
+    def __getattr__(self, name):
+        fn, index = getattr(self._lib, name), self._index
+
+        def call(*args):
+            if torch.cuda.current_device() == index:
+                return fn(*args)
+            with torch.cuda.device(index):
+                return fn(*args)
+        self.__dict__[name] = call            # resolved once per entry point
+        return call
+
+
 class BatchedBaseEnvironment(ABC):
     def __init__(self, config: str = "", batch: int = 1, device="cuda:0", seed: int = 0, auto_reset: bool = False,
                  first_env_id: int = 0):
@@ -111,7 +135,7 @@ class BatchedBaseEnvironment(ABC):
             raise _lib.CrlError("no CUDA device available (colosseumrl_b200 has no CPU fallback)")
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", index)
-        self._lib = _lib.init(index)
+        self._lib = _DeviceBoundLib(_lib.init(index), index)
         self.seed = int(seed)
         self.auto_reset = bool(auto_reset)
         self.first_env_id = int(first_env_id)     # global id of env 0 of this shard (Philox counter)
@@ -125,7 +149,7 @@ class BatchedBaseEnvironment(ABC):
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _check(self, rc):
-        _lib.check(rc, self._lib)
+        _lib.check(rc)
 
     def _dev(self, t, dtype):
         """Move an action tensor to the device (non-blocking from pinned host memory)."""
@@ -148,7 +172,9 @@ class BatchedBaseEnvironment(ABC):
     @property
     def stats(self) -> torch.Tensor:
         """Episode statistics int64 [NSTAT] (slots: include/colosseum_b200.h CRL_ST_*)."""
-        return self.stats_rows.sum(dim=0)
+        out = torch.empty((_lib.NSTAT,), dtype=torch.int64, device=self.device)
+        self._check(self._lib.crl_stats_reduce(self.stats_rows.data_ptr(), out.data_ptr(), 0, self._stream))
+        return out
 
     @property
     def flags(self):
@@ -215,7 +241,9 @@ class BatchedBaseEnvironment(ABC):
     def reset_stats(self):
         self.stats_rows.zero_()
 
-    def all_reduce_stats(self) -> torch.Tensor:
-        """Sum the episode statistics over all ranks (the only collective of the engine)."""
+    def all_reduce_stats(self, async_op: bool = False):
+        """Sum the episode statistics over all ranks (the only collective of the engine): one crl_stats_reduce launch
+        (256 rows -> the 32-slot vector) + one all-reduce of 256 bytes, both on the current stream.  async_op=True
+        returns (tensor, work handle) without waiting on the host."""
         from .sharding import all_reduce_stats
-        return all_reduce_stats(self.stats)
+        return all_reduce_stats(self.stats, async_op=async_op)

@@ -105,6 +105,13 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         self._check(self._lib.crl_blokus_reset(packed.data_ptr(), None, self.batch, self._stream))
         return BlokusBatchState(packed), torch.ones((self.batch,), dtype=torch.uint8, device=self.device)
 
+    def reset_where(self, state: BlokusBatchState, mask: torch.Tensor) -> BlokusBatchState:
+        """new_state for the games with mask != 0 (in place)."""
+        mask = self._dev(mask, torch.uint8)
+        self._check(self._lib.crl_blokus_reset(state.packed.data_ptr(), mask.data_ptr(), self.batch, self._stream))
+        state.result = None
+        return state
+
     def valid_actions(self, state: BlokusBatchState, player: int = -1,
                       out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, count_stats: bool = True):
         """valid_actions (:453-500): (counts int32 [B], ids int32 [B, capacity]) in the reference's order;

@@ -243,7 +243,10 @@ __device__ __forceinline__ int blk_any_move(BlkSmem &sm, int c, int round, uint3
     if (inv == 0u) return 0;
     const uint32_t rows = (uint32_t)blk_allowed_and_anchors<false>(sm, c, round, lane);
     if (rows == 0u) return 0;
-    if (inv & 1u) return 1;                                  // the monomino fits on every anchor (ANC is a subset of A)
+    // round 0: the anchor is the player's corner whatever it holds (board.py:177-179); every placement covers its
+    // anchor, so an occupied / blocked corner means no move at all (and no tree has to be built to find that out)
+    if (round == 0 && !__any_sync(0xffffffffu, lane < 20 && (sm.anc[lane] & (sm.A[lane] >> 4)) != 0u)) return 0;
+    if (inv & 1u) return 1;                                  // the monomino fits on every anchor that is an allowed cell
     if (!zeroed) { blk_zero_fit(sm, lane); zeroed = true; __syncwarp(); }  // (the common case never gets here)
     uint32_t ne = blk_tree_root(sm, lane);
     ne |= blk_tree_pass_le4(sm, ne, inv, lane);              // (this is the negative path: the whole tree is needed anyway)

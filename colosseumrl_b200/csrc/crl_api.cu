@@ -50,8 +50,8 @@ int crl_init(int device) {
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return fail(CRL_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
     if (prop.major != 10) return fail(CRL_ERR_UNSUPPORTED, "libcolosseum_b200 is built for sm_100a only (device is %s)", prop.name);
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(CRL_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    // (the caller's current device is left alone: launches go to the device that owns `stream`, and the host layer
+    // brackets every call with a device guard -- two environments on two GPUs in one process work)
 #endif
     return CRL_OK;
 }
@@ -63,6 +63,12 @@ int crl_philox_words(uint32_t *out, uint64_t seed, uint64_t first_env, uint32_t 
     CRL_LAUNCH(philox_words_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (uint4 *)out, (crl_u64)seed,
                (crl_u64)first_env, step, tag, (long long)B);
     return check_launch("philox_words_kernel");
+}
+
+int crl_stats_reduce(const int64_t *stats_rows, int64_t *out, int accumulate, crl_stream_t stream) {
+    if (!stats_rows || !out) return fail(CRL_ERR_ARG, "crl_stats_reduce: null pointer%s");
+    CRL_LAUNCH(stats_reduce_kernel, 1, 256, (cudaStream_t)stream, (const crl_u64 *)stats_rows, (crl_u64 *)out, accumulate);
+    return check_launch("stats_reduce_kernel");
 }
 
 /* ------------------------------------------------------------------------------------------- Tron */
@@ -78,7 +84,7 @@ static int tron_check(int N, int P, int64_t B) {
 // deterministic spawn_offset = 2 (:228, :222-224: randint(o, o + 1) == o).  The ring `ring_offset` cells in from the
 // wall is listed row-major, cut into four sides by the reference's slices, walked clockwise, split into P arcs
 // (np.array_split) and the element `len//2 + spawn_offset` (clamped to the arc) of each arc is the spawn.
-static int tron_starts(int N, int P, int ring_offset, int spawn_offset, int32_t *heads, int32_t *dirs) {
+static int tron_starts(int N, int P, int ring_offset, const int *spawn_offsets, int32_t *heads, int32_t *dirs) {
     const int half = N / 2, odd = N % 2;
     const double center = -0.5 * (odd - 1);
     const int r_in = half - ring_offset - 1, r_out = half - ring_offset, side = 2 * (r_in + 1);
@@ -113,6 +119,7 @@ static int tron_starts(int N, int P, int ring_offset, int spawn_offset, int32_t 
         arc((int)loop.size(), p, b, s);
         if (s <= 0) return CRL_ERR_ARG;
         auto clamp = [](int i, int size) { return i < 0 ? 0 : (i > size - 1 ? size - 1 : i); };   // get_centers :216-220
+        const int spawn_offset = spawn_offsets[p];               // one offset per player (:222-224)
         heads[p] = loop[b + clamp(s / 2 + spawn_offset, s)];
         arc(4 * side, p, b, s);
         if (s <= 0) return CRL_ERR_ARG;
@@ -124,9 +131,32 @@ static int tron_starts(int N, int P, int ring_offset, int spawn_offset, int32_t 
     return CRL_OK;
 }
 
-static int tron_params(int N, int P, TronParams &prm, int ring_offset = 1, int spawn_offset = 2) {
+static const int TRON_DEFAULT_SPAWNS[4] = {2, 2, 2, 2};           // new_state's default spawn_offset = 2 (:228)
+
+// TronParams of (N, P, ring_offset, per-player spawn offsets); the last few are cached per thread -- every API call
+// needs them and tron_starts walks the whole ring.
+static int tron_params_build(int N, int P, TronParams &prm, int ring_offset, const int *spawn_offsets);
+static int tron_params(int N, int P, TronParams &prm, int ring_offset = 1, const int *spawn_offsets = TRON_DEFAULT_SPAWNS) {
+    struct Entry { int N, P, ring, so[4]; bool ok; TronParams prm; };
+    static thread_local Entry cache[4];
+    static thread_local int next = 0;
+    for (int i = 0; i < 4; i++) {
+        const Entry &e = cache[i];
+        if (e.ok && e.N == N && e.P == P && e.ring == ring_offset && e.so[0] == spawn_offsets[0] && e.so[1] == spawn_offsets[1] &&
+            e.so[2] == spawn_offsets[2] && e.so[3] == spawn_offsets[3]) { prm = e.prm; return CRL_OK; }
+    }
+    int rc = tron_params_build(N, P, prm, ring_offset, spawn_offsets);
+    if (rc) return rc;
+    Entry &e = cache[next];
+    e.N = N; e.P = P; e.ring = ring_offset; e.ok = true; e.prm = prm;
+    for (int i = 0; i < 4; i++) e.so[i] = spawn_offsets[i];
+    next = (next + 1) & 3;
+    return CRL_OK;
+}
+
+static int tron_params_build(int N, int P, TronParams &prm, int ring_offset, const int *spawn_offsets) {
     int32_t heads[4] = {0, 0, 0, 0}, dirs[4] = {0, 0, 0, 0};
-    if (tron_starts(N, P, ring_offset, spawn_offset, heads, dirs) != CRL_OK)
+    if (tron_starts(N, P, ring_offset, spawn_offsets, heads, dirs) != CRL_OK)
         return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N / P / ring_offset / spawn_offset%s");
     prm.N = N; prm.P = P;
     prm.pmask = 0; prm.rkmask = (1u << (2 * P)) - 1u;
@@ -151,13 +181,13 @@ static int tron_params(int N, int P, TronParams &prm, int ring_offset = 1, int s
 typedef CUresult (*crl_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int tron_plane_map(const void *state, int64_t B, int tile, CUtensorMap *out) {
-    struct Entry { const void *p; int64_t B; int tile; CUtensorMap tm; };
+static int tron_plane_map(const void *state, int64_t B, int tile, int rows, CUtensorMap *out) {
+    struct Entry { const void *p; int64_t B; int tile, rows; CUtensorMap tm; };
     static thread_local Entry cache[8];
     static thread_local int next = 0;
     for (int i = 0; i < 8; i++)
-        if (cache[i].p == state && cache[i].B == B && cache[i].tile == tile) { *out = cache[i].tm; return CRL_OK; }
-    static crl_encode_fn encode = nullptr;
+        if (cache[i].p == state && cache[i].B == B && cache[i].tile == tile && cache[i].rows == rows) { *out = cache[i].tm; return CRL_OK; }
+    static thread_local crl_encode_fn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -165,19 +195,32 @@ static int tron_plane_map(const void *state, int64_t B, int tile, CUtensorMap *o
             return fail(CRL_ERR_CUDA, "cuTensorMapEncodeTiled is not available%s");
         encode = (crl_encode_fn)fn;
     }
-    cuuint64_t dims[2] = {(cuuint64_t)B * 4, 12};
+    cuuint64_t dims[2] = {(cuuint64_t)B * 4, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)B * 16};
-    cuuint32_t box[2] = {(cuuint32_t)tile * 4, 12};
+    cuuint32_t box[2] = {(cuuint32_t)tile * 4, (cuuint32_t)rows};
     cuuint32_t estr[2] = {1, 1};
     Entry &e = cache[next];
     CUresult r = encode(&e.tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(state), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { e.p = nullptr; return fail(CRL_ERR_CUDA, "cuTensorMapEncodeTiled failed%s"); }
-    e.p = state; e.B = B; e.tile = tile;
+    e.p = state; e.B = B; e.tile = tile; e.rows = rows;
     *out = e.tm;
     next = (next + 1) & 7;
     return CRL_OK;
+}
+
+// number of SMs of the current device (the persistent step kernel runs one CTA per SM)
+static int crl_sm_count() {
+    static thread_local int cached_dev = -1, cached_sms = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cached_dev = dev; cached_sms = sms;
+    }
+    return cached_sms;
 }
 #endif
 
@@ -196,57 +239,136 @@ int64_t crl_tron_state_bytes(int N, int P, int64_t B) {
     return (int64_t)TRON_VEC * 16 * B;
 }
 
-int crl_tron_start_positions_at(int N, int P, int ring_offset, int spawn_offset, int32_t *heads, int32_t *directions) {
-    int rc = tron_check(N, P, 0);
+// per-player spawn offsets -> the fixed-size array the helpers take (absent players: 0)
+static int tron_spawn_array(int P, const int32_t *spawn_offsets, int *so) {
+    if (!spawn_offsets) return fail(CRL_ERR_ARG, "tron: null spawn_offsets%s");
+    for (int p = 0; p < 4; p++) so[p] = p < P ? (int)spawn_offsets[p] : 0;
+    return CRL_OK;
+}
+
+int crl_tron_start_positions_spawns(int N, int P, int ring_offset, const int32_t *spawn_offsets, int32_t *heads,
+                                    int32_t *directions) {
+    int rc = tron_check(N, P, 0), so[4];
     if (rc) return rc;
     if (!heads || !directions) return fail(CRL_ERR_ARG, "crl_tron_start_positions: null pointer%s");
-    if (tron_starts(N, P, ring_offset, spawn_offset, heads, directions))
+    if ((rc = tron_spawn_array(P, spawn_offsets, so))) return rc;
+    if (tron_starts(N, P, ring_offset, so, heads, directions))
         return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N / P / ring_offset / spawn_offset%s");
     return CRL_OK;
+}
+
+int crl_tron_start_positions_at(int N, int P, int ring_offset, int spawn_offset, int32_t *heads, int32_t *directions) {
+    const int32_t so[4] = {spawn_offset, spawn_offset, spawn_offset, spawn_offset};
+    return crl_tron_start_positions_spawns(N, P, ring_offset, so, heads, directions);
 }
 
 int crl_tron_start_positions(int N, int P, int32_t *heads, int32_t *directions) {
     return crl_tron_start_positions_at(N, P, 1, 2, heads, directions);
 }
 
-int crl_tron_reset_at(void *state, const uint8_t *mask, int64_t B, int N, int P, int ring_offset, int spawn_offset,
-                      crl_stream_t stream) {
-    int rc = tron_check(N, P, B);
+int crl_tron_reset_spawns(void *state, const uint8_t *mask, int64_t B, int N, int P, int ring_offset,
+                          const int32_t *spawn_offsets, crl_stream_t stream) {
+    int rc = tron_check(N, P, B), so[4];
     if (rc) return rc;
     if (!state) return fail(CRL_ERR_ARG, "crl_tron_reset: null state%s");
+    if ((rc = tron_spawn_array(P, spawn_offsets, so))) return rc;
     TronParams prm;
-    if ((rc = tron_params(N, P, prm, ring_offset, spawn_offset))) return rc;
+    if ((rc = tron_params(N, P, prm, ring_offset, so))) return rc;
     if (B == 0) return CRL_OK;
     CRL_LAUNCH(tron_reset_kernel, blocks_for(B * TRON_VEC, 256), 256, (cudaStream_t)stream, (uint4 *)state, mask, (long long)B, prm);
     return check_launch("tron_reset_kernel");
+}
+
+int crl_tron_reset_at(void *state, const uint8_t *mask, int64_t B, int N, int P, int ring_offset, int spawn_offset,
+                      crl_stream_t stream) {
+    const int32_t so[4] = {spawn_offset, spawn_offset, spawn_offset, spawn_offset};
+    return crl_tron_reset_spawns(state, mask, B, N, P, ring_offset, so, stream);
 }
 
 int crl_tron_reset(void *state, const uint8_t *mask, int64_t B, int N, int P, crl_stream_t stream) {
     return crl_tron_reset_at(state, mask, B, N, P, 1, 2, stream);
 }
 
+static int tron_step_impl(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, int64_t *stats,
+                          int64_t B, int N, int P, int flags, int ring_offset, const int *so, crl_stream_t stream);
+
 int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, int64_t *stats,
                   int64_t B, int N, int P, int flags, crl_stream_t stream) {
+    return tron_step_impl(state_in, state_out, actions, result, stats, B, N, P, flags, 1, TRON_DEFAULT_SPAWNS, stream);
+}
+
+int crl_tron_step_spawns(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, int64_t *stats,
+                         int64_t B, int N, int P, int flags, int ring_offset, const int32_t *spawn_offsets,
+                         crl_stream_t stream) {
+    int rc = tron_check(N, P, B), so[4];
+    if (rc) return rc;
+    if ((rc = tron_spawn_array(P, spawn_offsets, so))) return rc;
+    return tron_step_impl(state_in, state_out, actions, result, stats, B, N, P, flags, ring_offset, so, stream);
+}
+
+}  // extern "C"
+
+static int tron_step_impl(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, int64_t *stats,
+                          int64_t B, int N, int P, int flags, int ring_offset, const int *so, crl_stream_t stream) {
+
     int rc = tron_check(N, P, B);
     if (rc) return rc;
     if (!state_in || !state_out || !actions || !result) return fail(CRL_ERR_ARG, "crl_tron_step: null pointer%s");
     TronParams prm;
-    if ((rc = tron_params(N, P, prm))) return rc;
+    if ((rc = tron_params(N, P, prm, ring_offset, so))) return rc;
     if (B == 0) return CRL_OK;
     if (((uintptr_t)state_in | (uintptr_t)state_out) & 15) return fail(CRL_ERR_ARG, "crl_tron_step: state buffers must be 16-byte aligned%s");
     if (B > (INT32_MAX >> 2)) return fail(CRL_ERR_UNSUPPORTED, "crl_tron_step: batch too large for one launch%s");
-    const int tile = tron_tile();
-    TronMaps maps;
-#ifndef CRL_HOSTSIM
-    if ((rc = tron_plane_map(state_in, B, tile, &maps.in))) return rc;
-    if ((rc = tron_plane_map(state_out, B, tile, &maps.out))) return rc;
-#else
-    maps.unused = 0;
-#endif
     // Programmatic dependent launch: the kernel waits (griddepcontrol.wait) for its predecessor's completion before
-    // it touches memory, and lets its successor's CTAs become resident once its own planes are on their way back.
+    // it touches memory, and lets its successor's CTAs become resident once its own tiles are on their way back.
     // Only launches carrying the attribute may start early, so ordering against any other kernel is unchanged.
     static const bool use_pdl = !(getenv("CRL_PDL") && atoi(getenv("CRL_PDL")) == 0);
+    // CRL_TRON_KERNEL=cta selects the round-1 kernel (one 64-env tile per CTA) for A/B measurements
+    static const bool warp_kernel = !(getenv("CRL_TRON_KERNEL") && !strcmp(getenv("CRL_TRON_KERNEL"), "cta"));
+    TronMaps maps;
+    if (warp_kernel) {
+#ifndef CRL_HOSTSIM
+        constexpr int NW = 16;
+        if ((rc = tron_plane_map(state_in, B, TRON_WTILE, TRON_VEC, &maps.in))) return rc;
+        if ((rc = tron_plane_map(state_out, B, TRON_WTILE, TRON_VEC, &maps.out))) return rc;
+        const int ntiles = (int)((B + TRON_WTILE - 1) / TRON_WTILE), sms = crl_sm_count();
+        // one CTA per SM while every worker gets at most one tile; two per SM (they fit: 2 x 104 KB) for larger batches
+        const int grid = ntiles <= sms * NW ? (ntiles < sms ? ntiles : sms) : (2 * sms < (ntiles + NW - 1) / NW ? 2 * sms : (ntiles + NW - 1) / NW);
+        const size_t smem = NW * sizeof(TronTile<TRON_WTILE>);
+        static thread_local int attr_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (attr_dev != dev) {
+            if (cudaFuncSetAttribute(tron_step_warp_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return check_launch("cudaFuncSetAttribute(tron_step_warp_kernel)");
+            attr_dev = dev;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * NW); cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, tron_step_warp_kernel<NW>, maps, (const uint32_t *)actions, (uint2 *)result,
+                           (crl_u64 *)stats, (long long)B, prm, flags, ntiles);
+#else
+        constexpr int NW = 2;                                    // emulator: 64 host threads, 3 CTAs
+        maps.in_ptr = (const uint4 *)state_in; maps.out_ptr = (uint4 *)state_out;
+        const int ntiles = (int)((B + TRON_WTILE - 1) / TRON_WTILE);
+        const int grid = ntiles < 3 ? ntiles : 3;
+        CRL_LAUNCH(tron_step_warp_kernel<NW>, grid, 32 * NW, (cudaStream_t)stream, maps, (const uint32_t *)actions,
+                   (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags, ntiles);
+#endif
+        return check_launch("tron_step_warp_kernel");
+    }
+    const int tile = tron_tile();
+#ifndef CRL_HOSTSIM
+    if ((rc = tron_plane_map(state_in, B, tile, 12, &maps.in))) return rc;
+    if ((rc = tron_plane_map(state_out, B, tile, 12, &maps.out))) return rc;
+#else
+    maps.in_ptr = (const uint4 *)state_in; maps.out_ptr = (uint4 *)state_out;
+#endif
 #define TRON_STEP_ARGS maps, (const uint4 *)state_in, (uint4 *)state_out, (const uint32_t *)actions, (uint2 *)result, \
                        (crl_u64 *)stats, (long long)B, prm, flags
 #define TRON_STEP_LAUNCH(T)                                                                                         \
@@ -260,6 +382,8 @@ int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, 
 #undef TRON_STEP_ARGS
     return check_launch("tron_step_kernel");
 }
+
+extern "C" {
 
 int crl_tron_policy_random(int8_t *actions, uint64_t seed, uint64_t first_env, uint32_t step, int64_t B,
                            crl_stream_t stream) {

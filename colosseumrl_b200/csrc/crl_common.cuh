@@ -134,6 +134,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int x, int y
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                  :: "l"(tm), "r"(x), "r"(y), "r"(smem_u32(src_smem)) : "memory");
 }
+__device__ __forceinline__ void tensormap_prefetch(const CUtensorMap *tm) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(tm) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit_wait_read() {
@@ -161,6 +164,23 @@ __device__ __forceinline__ void pdl_wait() {   // blocks until the predecessor g
 __device__ __forceinline__ void stats_flush_row(const int *sm, crl_u64 *g) {
     if (threadIdx.x < CRL_NSTAT && sm[threadIdx.x] != 0)
         atomicAdd(g + (blockIdx.x & (CRL_STAT_ROWS - 1)) * CRL_NSTAT + threadIdx.x, (crl_u64)(long long)sm[threadIdx.x]);
+}
+
+// reader side: out[s] (+)= sum over the CRL_STAT_ROWS rows of rows[r][s]; one CTA of 256 threads (8 x 32 rows each)
+__global__ void __launch_bounds__(256) stats_reduce_kernel(const crl_u64 *__restrict__ rows, crl_u64 *__restrict__ out,
+                                                           int accumulate) {
+    __shared__ crl_u64 part[8][CRL_NSTAT];
+    const int slot = threadIdx.x & (CRL_NSTAT - 1), grp = threadIdx.x >> 5;
+    crl_u64 s = 0;
+#pragma unroll 8
+    for (int r = grp * (CRL_STAT_ROWS / 8); r < (grp + 1) * (CRL_STAT_ROWS / 8); r++) s += rows[r * CRL_NSTAT + slot];
+    part[grp][slot] = s;
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+        for (int g = 1; g < 8; g++) s += part[g][slot];
+        out[slot] = accumulate ? out[slot] + s : s;
+    }
 }
 
 struct BlockStats {

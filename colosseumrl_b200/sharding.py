@@ -20,9 +20,11 @@ def shard_range(total_envs: int, rank: int, world: int) -> Tuple[int, int]:
     return first, base + (1 if rank < rem else 0)
 
 
-def all_reduce_stats(stats: torch.Tensor) -> torch.Tensor:
-    """SUM over ranks of the statistics vector (returns a new tensor; identity when not distributed)."""
-    out = stats.clone()
+def all_reduce_stats(stats: torch.Tensor, async_op: bool = False):
+    """SUM over ranks of the statistics vector, in place on `stats` (a fresh reduction of the device rows when it comes
+    from `env.stats`); identity when not distributed.  async_op=True: returns (tensor, work) -- `work.wait()` orders
+    the current stream after the collective without blocking the host (None when there is nothing to wait for)."""
+    work = None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(out, op=dist.ReduceOp.SUM)
-    return out
+        work = dist.all_reduce(stats, op=dist.ReduceOp.SUM, async_op=async_op)
+    return (stats, work) if async_op else stats

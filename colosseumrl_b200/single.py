@@ -247,8 +247,8 @@ class BlokusEnvironment(SingleEnvironment):
         return _blokus.action_to_string(_blokus.player_perspective_action_to_real(_blokus.string_to_action(player_action), player))
 
     def is_valid_action(self, state, player: int, action: str) -> bool:
-        if len(action) == 0:
-            return True
+        if len(action) == 0:                   # '' is not a valid action here either (BlokusEnvironment.py:702,
+            return False                       # tictactoe_2p_env.py:372); match_server special-cases it itself
         try:
             aid = _blokus.string_to_action(action)
         except (ValueError, KeyError, IndexError):
@@ -307,8 +307,8 @@ class _TicTacToe(SingleEnvironment):
         return [str(tuple(int(i) for i in np.unravel_index(c, self._shape))) for c in cells]
 
     def is_valid_action(self, state, player: int, action: str) -> bool:
-        if len(action) == 0:
-            return True
+        if len(action) == 0:                   # '' is not a valid action here either (BlokusEnvironment.py:702,
+            return False                       # tictactoe_2p_env.py:372); match_server special-cases it itself
         try:
             c = self._index(action)
         except ValueError:

@@ -48,6 +48,13 @@ class _BatchedTicTacToe(BatchedBaseEnvironment):
         players = torch.ones((self.batch,), dtype=torch.uint8, device=self.device)      # player 0 moves first
         return TTTBatchState(packed), players
 
+    def reset_where(self, state: TTTBatchState, mask: torch.Tensor) -> TTTBatchState:
+        """new_state for the environments with mask != 0 (in place)."""
+        mask = self._dev(mask, torch.uint8)
+        self._check(self._lib.crl_ttt_reset(state.packed.data_ptr(), mask.data_ptr(), self.batch, self.N_PLAYERS, self._stream))
+        state.valid = None                     # the cached empty-cell masks no longer describe the reset boards
+        return state
+
     def next_state(self, state: TTTBatchState, players, actions, out: Optional[TTTBatchState] = None):
         """next_state (2p :240-315).  actions: int8 [B], C-order flat cell index, negative = '' (pass).
         Returns (new_state, new_players mask, reward int8 [B] (the mover's), terminal uint8 [B], winners mask uint8 [B])."""

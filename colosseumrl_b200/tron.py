@@ -49,6 +49,8 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         self.N, self.num_players, self.observation_window, self.remove_on_death = parse_tron_config(config)
         if self._lib.crl_tron_state_bytes(self.N, self.num_players, self.batch) < 0:
             raise _lib.CrlError(self._lib.crl_last_error().decode())
+        # the spawns of the last new_state(): auto-reset inside the step restarts finished games from the same ones
+        self._ring_offset, self._spawn_offsets = 1, None          # None = the reference's defaults (1, 2)
 
     @classmethod
     def create(cls, board_size: int = 19, num_players: int = 4, observation_window: int = -1,
@@ -80,36 +82,69 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
     def _alloc(self):
         return torch.empty((13, self.batch, 4), dtype=torch.int32, device=self.device)
 
+    def _spawn_array(self, spawn_offset):
+        """spawn_offset as new_state takes it -> one int per player: an int is used for every player; a (lo, hi) tuple
+        draws np.random.randint(lo, hi) once PER PLAYER like the reference (:222-224); a list gives them explicitly."""
+        import ctypes as C
+        import numpy as np
+        P = self.num_players
+        if isinstance(spawn_offset, (int, np.integer)):
+            offs = [int(spawn_offset)] * P
+        elif isinstance(spawn_offset, tuple) and len(spawn_offset) == 2:
+            offs = [int(np.random.randint(*spawn_offset)) for _ in range(P)]
+        else:
+            offs = [int(o) for o in spawn_offset]
+            if len(offs) != P:
+                raise ValueError("spawn_offset list must have one entry per player")
+        return (C.c_int32 * P)(*offs)
+
     def new_state(self, num_players: int = None, ring_offset: int = 1, spawn_offset=2,
                   out: Optional[TronBatchState] = None):
         """TronGridEnvironment.new_state (:228-263) for every environment of the batch.  ring_offset / spawn_offset as
-        in the reference (generate_start_positions :183-226); a (lo, hi) tuple draws ONE offset per player list entry
-        like the reference does (np.random.randint(lo, hi), :222-224) -- here a single draw shared by the players
-        and the batch, taken on the host."""
+        in the reference (generate_start_positions :183-226): an int shifts every player's spawn, a (lo, hi) tuple
+        draws one offset PER PLAYER (np.random.randint(lo, hi), :222-224; the draw is taken on the host and shared by
+        the batch), a list of P ints sets them explicitly.  The environment remembers the spawns: auto-reset restarts
+        finished games from them."""
         assert num_players is None or num_players == self.num_players, \
             "Do not change the number of players from the game configuration."
-        if not isinstance(spawn_offset, int):
-            import numpy as np
-            spawn_offset = int(np.random.randint(*spawn_offset))
+        so = self._spawn_array(spawn_offset)
         packed = out.packed if out is not None else self._alloc()
-        self._check(self._lib.crl_tron_reset_at(packed.data_ptr(), None, self.batch, self.N, self.num_players,
-                                                int(ring_offset), int(spawn_offset), self._stream))
+        self._check(self._lib.crl_tron_reset_spawns(packed.data_ptr(), None, self.batch, self.N, self.num_players,
+                                                    int(ring_offset), so, self._stream))
+        default = int(ring_offset) == 1 and all(o == 2 for o in so)
+        self._ring_offset, self._spawn_offsets = int(ring_offset), (None if default else so)
         players = torch.full((self.batch,), (1 << self.num_players) - 1, dtype=torch.uint8, device=self.device)
         return TronBatchState(packed), players
 
-    def generate_start_positions(self, ring_offset: int = 1, spawn_offset: int = 0):
+    def generate_start_positions(self, ring_offset: int = 1, spawn_offset=0):
         """generate_start_positions (:183-226): (heads = y * N + x, directions) as int64 numpy arrays."""
         import ctypes as C
         import numpy as np
         h, d = (C.c_int32 * 4)(), (C.c_int32 * 4)()
-        self._check(self._lib.crl_tron_start_positions_at(self.N, self.num_players, int(ring_offset), int(spawn_offset), h, d))
+        self._check(self._lib.crl_tron_start_positions_spawns(self.N, self.num_players, int(ring_offset),
+                                                              self._spawn_array(spawn_offset), h, d))
         return (np.array(h[:self.num_players], np.int64), np.array(d[:self.num_players], np.int64))
 
     def reset_where(self, state: TronBatchState, mask: torch.Tensor):
         mask = self._dev(mask, torch.uint8)
-        self._check(self._lib.crl_tron_reset(state.packed.data_ptr(), mask.data_ptr(), self.batch, self.N,
-                                             self.num_players, self._stream))
+        if self._spawn_offsets is None:
+            self._check(self._lib.crl_tron_reset(state.packed.data_ptr(), mask.data_ptr(), self.batch, self.N,
+                                                 self.num_players, self._stream))
+        else:
+            self._check(self._lib.crl_tron_reset_spawns(state.packed.data_ptr(), mask.data_ptr(), self.batch, self.N,
+                                                        self.num_players, self._ring_offset, self._spawn_offsets,
+                                                        self._stream))
+        state.result = None                     # the record of the step before the reset no longer describes `state`
         return state
+
+    def _step_call(self, src, dst, actions_ptr, result_ptr, flags):
+        """crl_tron_step, or crl_tron_step_spawns when new_state() was given non-default spawns (auto-reset uses them)."""
+        if self._spawn_offsets is None:
+            return self._lib.crl_tron_step(src, dst, actions_ptr, result_ptr, self._stats_ptr, self.batch, self.N,
+                                           self.num_players, flags, self._stream)
+        return self._lib.crl_tron_step_spawns(src, dst, actions_ptr, result_ptr, self._stats_ptr, self.batch, self.N,
+                                              self.num_players, flags, self._ring_offset, self._spawn_offsets,
+                                              self._stream)
 
     def next_state(self, state: TronBatchState, players, actions, out: Optional[TronBatchState] = None):
         """TronGridEnvironment.next_state (:265-323).  actions: int8 [B, 4] (0 forward, 1 right, -1 left; entries of
@@ -127,9 +162,8 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         new = out if out is not None else TronBatchState(self._alloc())
         if new.result is None:
             new.result = self._new_result((self.batch, 8))
-        self._check(self._lib.crl_tron_step(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
-                                            new.result.data_ptr(), self._stats_ptr, self.batch, self.N,
-                                            self.num_players, self.flags, self._stream))
+        self._check(self._step_call(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
+                                    new.result.data_ptr(), self.flags))
         return new
 
     def host_stepper(self, state: TronBatchState, stream=None, compact=False, packed_actions: bool = False):
@@ -149,9 +183,8 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
             (_lib.FLAG_PACKED_ACTIONS if packed_actions else 0)
 
         def step(dev_actions):
-            self._check(self._lib.crl_tron_step(state.packed.data_ptr(), state.packed.data_ptr(), dev_actions.data_ptr(),
-                                                rec.data_ptr(), self._stats_ptr, self.batch, self.N, self.num_players,
-                                                flags, self._stream))
+            self._check(self._step_call(state.packed.data_ptr(), state.packed.data_ptr(), dev_actions.data_ptr(),
+                                        rec.data_ptr(), flags))
             state.result = None                 # the full record of an earlier step no longer describes `state`
             return rec
         if packed_actions:

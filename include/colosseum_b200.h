@@ -66,6 +66,12 @@ int crl_init(int device);
 int crl_philox_words(uint32_t *out, uint64_t seed, uint64_t first_env, uint32_t step, uint32_t tag, int64_t B,
                      crl_stream_t stream);
 
+/* Reader side of the statistics buffer: out[s] = sum over the CRL_STAT_ROWS rows of stats_rows[r][s]
+ * (out = int64[CRL_NSTAT] on the device; accumulate != 0: out[s] += ...).  One tiny launch; the 32-slot vector is what a
+ * multi-GPU job all-reduces (NCCL) once per measurement window -- the engine's only collective (SURVEY.md section 8e;
+ * the reference has no counterpart: its statistics are Python-side counters in the callers' loops). */
+int crl_stats_reduce(const int64_t *stats_rows, int64_t *out, int accumulate, crl_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------- Tron
  * Packed state: 208 bytes per environment, SoA [13][B] of 16-byte vectors (csrc/tron.cuh).
  * Supported: 5 <= N <= 19 (N*N <= 384), 2 <= P <= 4.
@@ -89,12 +95,23 @@ int crl_tron_start_positions(int N, int P, int32_t *heads, int32_t *directions);
 int crl_tron_reset(void *state, const uint8_t *mask_or_null, int64_t B, int N, int P, crl_stream_t stream);
 /* The same two with new_state's optional arguments (TronGridEnvironment.py:228: ring_offset = how far in from the wall
  * the spawn ring lies, spawn_offset = shift of every spawn along its arc; the defaults are 1 and 2).  An integer
- * spawn_offset is deterministic in the reference (:222-224); its random (lo, hi) tuple form is the caller's business:
- * draw the offset on the host and pass it.  CRL_ERR_ARG if the ring is degenerate for this N / P.  Auto-reset
- * inside the step kernels (CRL_FLAG_AUTO_RESET) always restarts from the default new_state(). */
+ * spawn_offset is deterministic in the reference (:222-224: randint(o, o + 1) == o for every player).
+ * CRL_ERR_ARG if the ring is degenerate for this N / P. */
 int crl_tron_start_positions_at(int N, int P, int ring_offset, int spawn_offset, int32_t *heads, int32_t *directions);
 int crl_tron_reset_at(void *state, const uint8_t *mask_or_null, int64_t B, int N, int P, int ring_offset, int spawn_offset,
                       crl_stream_t stream);
+/* ... and with ONE OFFSET PER PLAYER, the reference's (lo, hi) tuple form: generate_start_positions draws
+ * `offsets = [np.random.randint(lo, hi) for _ in range(num_players)]` (:222-224) and uses offsets[p] for player p's
+ * head and direction.  spawn_offsets = int32[P] on the HOST (the draw is the caller's: numpy's global RNG seeded from
+ * the wall clock, :255, is not reproducible by design).  crl_tron_step_spawns is crl_tron_step whose auto-reset
+ * (CRL_FLAG_AUTO_RESET) restarts finished games from THESE spawns instead of the default new_state(). */
+int crl_tron_start_positions_spawns(int N, int P, int ring_offset, const int32_t *spawn_offsets, int32_t *heads,
+                                    int32_t *directions);
+int crl_tron_reset_spawns(void *state, const uint8_t *mask_or_null, int64_t B, int N, int P, int ring_offset,
+                          const int32_t *spawn_offsets, crl_stream_t stream);
+int crl_tron_step_spawns(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, int64_t *stats,
+                         int64_t B, int N, int P, int flags, int ring_offset, const int32_t *spawn_offsets,
+                         crl_stream_t stream);
 /* next_state (TronGridEnvironment.py:265-323 -> CyTronGrid.pyx:3-62) + compute_ranking (:483-508).
  * state_out may equal state_in (in place). stats may be NULL. */
 int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result,

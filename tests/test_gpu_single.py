@@ -65,7 +65,7 @@ def test_blokus_game_through_strings():
             exp = [action_to_string(int(a)) for a in g["valid_flat"][g["valid_off"][i]:g["valid_off"][i + 1]]] or [""]
             assert env.valid_actions(state, mover) == exp
         action = action_to_string(int(g["action"][i]))
-        assert env.is_valid_action(state, mover, action)
+        assert env.is_valid_action(state, mover, action) == (action != "")     # '' is never "valid" (reference :702)
         new, players, rewards, terminal, winners = env.next_state(state, [mover], [action])
         assert (new[0].board_contents == g["board"][i]).all() and new[1] == g["round"][i]
         assert [pl.player_score for pl in new[2]] == list(g["scores"][i])
@@ -170,6 +170,62 @@ def test_vector_env():
         per = [env.state_to_observation(v.state, p)["board"] for p in range(4)]
         exp = torch.stack([per[int(mover[g])][g] for g in range(128)])
         assert (obs["board"] == exp).all()
+
+
+def test_vector_env_episode_boundary():
+    """auto_reset: the step that ends an episode already returns the FRESH game's observation, mover and valid actions
+    (what the next action is applied to), and the finished board is available as info["final_observation"]."""
+    import torch
+    from colosseumrl_b200 import BatchedTronGridEnvironment, BatchedBlokusEnvironment, BatchedTicTacToe4PlayerEnv
+    from colosseumrl_b200.vector import VectorEnv
+    # Tic Tac Toe 4p: a finished game shows the empty board, mover 0 and all 27 cells valid; a full-board draw does not
+    # leave a zero mask behind (the agent is never forced to pass on a fresh board)
+    env = BatchedTicTacToe4PlayerEnv("", batch=256, auto_reset=True, seed=5)
+    v = VectorEnv(env)
+    v.reset()
+    ended = 0
+    for t in range(60):
+        act = env.random_actions(v.state, t)
+        prev_valid = v.valid_actions().clone()
+        assert (prev_valid != 0).all()                       # never a forced pass
+        assert (((prev_valid >> act.to(torch.int32)) & 1) == 1).all()      # the policy's cell is free on the board we showed
+        obs, rewards, dones, info = v.step(act, final_observation=True)
+        d = dones.bool()
+        if d.any():
+            ended += int(d.sum())
+            assert (obs["board"][d] == -1).all() and (info["mover"][d] == 0).all()
+            assert (v.valid_actions()[d] == (1 << 27) - 1).all()
+            assert (info["final_observation"]["board"][d] != -1).any(dim=(1, 2, 3)).all()
+        assert not env.is_terminal(v.state).any()
+    assert ended > 100
+    # Blokus: after the terminal step the mover's list is the fresh board's 116 openings
+    env = BatchedBlokusEnvironment("", batch=16, auto_reset=True, seed=2)
+    v = VectorEnv(env)
+    v.reset()
+    ended = 0
+    for t in range(90):
+        valid = v.valid_actions()
+        obs, rewards, dones, info = v.step(env.random_actions(valid, t))
+        d = dones.bool()
+        if d.any():
+            ended += int(d.sum())
+            assert (obs["board"][d] == -1).all() and (info["mover"][d] == 0).all()
+            counts, _ = v.valid_actions()
+            assert (counts[d] == 116).all()
+    assert ended >= 8
+    # Tron: every seat sees the start position again
+    env = BatchedTronGridEnvironment("", batch=64, auto_reset=True, seed=4)
+    v = VectorEnv(env)
+    first = v.reset()
+    ended = 0
+    for t in range(40):
+        obs, rewards, dones, info = v.step(env.random_actions(t))
+        d = dones.bool()
+        if d.any():
+            ended += int(d.sum())
+            assert (obs["board"][d] == first["board"][d]).all() and (obs["deaths"][d] == 0).all()
+            assert (info["players"][d] == 15).all()
+    assert ended > 0
 
 
 def test_blokus_valid_actions_dict_and_current_rewards():

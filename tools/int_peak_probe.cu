@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed) {
     if (r == 0x12345678u) out[0] = r;
 }
 
+static double g_rate[8];   // warp-inst / clk / SM per kind (for the JSON line)
+
 template <int KIND>
 int run(const char *name, double inst_per_iter, int sms, double mhz) {
     uint32_t *out;
@@ -60,6 +62,7 @@ int run(const char *name, double inst_per_iter, int sms, double mhz) {
     const double rate = warp_inst / (best * 1e-3);
     printf("%-28s %8.3f ms  %7.2f T warp-inst/s  %5.2f warp-inst / clk / SM (at %.0f MHz)\n", name, best, rate / 1e12,
            rate / (sms * mhz * 1e6), mhz);
+    g_rate[KIND] = rate / (sms * mhz * 1e6);
     cudaFree(out);
     return 0;
 }
@@ -75,5 +78,11 @@ int main() {
     const int s = p.multiProcessorCount;
     run<0>("LOP3", 1, s, mhz); run<1>("SHF", 1, s, mhz); run<2>("IADD", 1, s, mhz); run<3>("IMAD", 1, s, mhz);
     run<4>("POPC + LOP3 + IADD", 3, s, mhz); run<5>("LDS + IADD + LOP3", 3, s, mhz); run<6>("SHF + IADD + 2 LOP3 mix", 4, s, mhz);
+    // one JSON line (stderr) for INT_PEAKS.json: the issue roof bench.py reports Blokus against
+    fprintf(stderr, "{\"gpu\": \"%s\", \"sms\": %d, \"sm_mhz\": %.0f, \"issue_warp_inst_per_clk_per_sm\": 4, "
+                    "\"issue_peak_t_warp_inst_s\": %.4f, \"lop3\": %.3f, \"shf\": %.3f, \"iadd\": %.3f, \"imad\": %.3f, "
+                    "\"popc_lop3_iadd\": %.3f, \"lds_iadd_lop3\": %.3f, \"mix_warp_inst_per_clk_per_sm\": %.3f, "
+                    "\"how\": \"tools/int_peak_probe.cu: long independent chains, 8 CTAs x 256 threads per SM, best of 5, CUDA events\"}\n",
+            p.name, s, mhz, 4.0 * s * mhz * 1e6 / 1e12, g_rate[0], g_rate[1], g_rate[2], g_rate[3], g_rate[4], g_rate[5], g_rate[6]);
     return 0;
 }
