@@ -50,7 +50,7 @@ POLICY = "philox4x32-10 uniform random, auto-reset"
 WORKLOADS = {
     # name: description, per-GPU batch, algorithmic bytes per env-step, state bytes per env
     "tron": dict(desc="Tron 4-player 19x19, 65,536 batched envs, random actions (BASELINE.json configs[1])",
-                 B=65536, bytes=424, state=208, kernel="tron_step_warp_kernel", launches=1, dtype="u32"),
+                 B=65536, bytes=424, state=208, kernel="tron_step_kernel", launches=1, dtype="u32"),
     "blokus": dict(desc="Blokus 4-player 20x20, valid_actions + next_state over 16,384 batched games (BASELINE.json configs[2])",
                    B=16384, bytes=2196, state=352, kernel="blokus_legal_kernel", launches=3, dtype="u32"),
     "ttt4": dict(desc="Tic Tac Toe 4-player 3x3x3, 1,048,576 batched envs, random self-play (BASELINE.json configs[3])",

@@ -210,18 +210,6 @@ static int tron_plane_map(const void *state, int64_t B, int tile, int rows, CUte
     return CRL_OK;
 }
 
-// number of SMs of the current device (the persistent step kernel runs one CTA per SM)
-static int crl_sm_count() {
-    static thread_local int cached_dev = -1, cached_sms = 0;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (dev != cached_dev) {
-        int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        cached_dev = dev; cached_sms = sms;
-    }
-    return cached_sms;
-}
 #endif
 
 // environments (= threads) per CTA of the step / rollout kernels: 64 (13 KB of shared memory, ~7 CTAs per SM at
@@ -319,49 +307,10 @@ static int tron_step_impl(const void *state_in, void *state_out, const int8_t *a
     if (B == 0) return CRL_OK;
     if (((uintptr_t)state_in | (uintptr_t)state_out) & 15) return fail(CRL_ERR_ARG, "crl_tron_step: state buffers must be 16-byte aligned%s");
     if (B > (INT32_MAX >> 2)) return fail(CRL_ERR_UNSUPPORTED, "crl_tron_step: batch too large for one launch%s");
-    // Programmatic dependent launch: the kernel waits (griddepcontrol.wait) for its predecessor's completion before
-    // it touches memory, and lets its successor's CTAs become resident once its own tiles are on their way back.
+    // Programmatic dependent launch: the kernel prefetches its tile into L2, waits (griddepcontrol.wait) for its
+    // predecessor's completion before it reads anything, and lets its successor's CTAs become resident right after.
     // Only launches carrying the attribute may start early, so ordering against any other kernel is unchanged.
-    static const bool use_pdl = !(getenv("CRL_PDL") && atoi(getenv("CRL_PDL")) == 0);
-    // CRL_TRON_KERNEL=cta selects the round-1 kernel (one 64-env tile per CTA) for A/B measurements
-    static const bool warp_kernel = !(getenv("CRL_TRON_KERNEL") && !strcmp(getenv("CRL_TRON_KERNEL"), "cta"));
     TronMaps maps;
-    if (warp_kernel) {
-#ifndef CRL_HOSTSIM
-        constexpr int NW = 16;
-        if ((rc = tron_plane_map(state_in, B, TRON_WTILE, TRON_VEC, &maps.in))) return rc;
-        if ((rc = tron_plane_map(state_out, B, TRON_WTILE, TRON_VEC, &maps.out))) return rc;
-        const int ntiles = (int)((B + TRON_WTILE - 1) / TRON_WTILE), sms = crl_sm_count();
-        // one CTA per SM while every worker gets at most one tile; two per SM (they fit: 2 x 104 KB) for larger batches
-        const int grid = ntiles <= sms * NW ? (ntiles < sms ? ntiles : sms) : (2 * sms < (ntiles + NW - 1) / NW ? 2 * sms : (ntiles + NW - 1) / NW);
-        const size_t smem = NW * sizeof(TronTile<TRON_WTILE>);
-        static thread_local int attr_dev = -1;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (attr_dev != dev) {
-            if (cudaFuncSetAttribute(tron_step_warp_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return check_launch("cudaFuncSetAttribute(tron_step_warp_kernel)");
-            attr_dev = dev;
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * NW); cfg.dynamicSmemBytes = smem;
-        cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
-        cudaLaunchKernelEx(&cfg, tron_step_warp_kernel<NW>, maps, (const uint32_t *)actions, (uint2 *)result,
-                           (crl_u64 *)stats, (long long)B, prm, flags, ntiles);
-#else
-        constexpr int NW = 2;                                    // emulator: 64 host threads, 3 CTAs
-        maps.in_ptr = (const uint4 *)state_in; maps.out_ptr = (uint4 *)state_out;
-        const int ntiles = (int)((B + TRON_WTILE - 1) / TRON_WTILE);
-        const int grid = ntiles < 3 ? ntiles : 3;
-        CRL_LAUNCH(tron_step_warp_kernel<NW>, grid, 32 * NW, (cudaStream_t)stream, maps, (const uint32_t *)actions,
-                   (uint2 *)result, (crl_u64 *)stats, (long long)B, prm, flags, ntiles);
-#endif
-        return check_launch("tron_step_warp_kernel");
-    }
     const int tile = tron_tile();
 #ifndef CRL_HOSTSIM
     if ((rc = tron_plane_map(state_in, B, tile, 12, &maps.in))) return rc;
@@ -373,8 +322,7 @@ static int tron_step_impl(const void *state_in, void *state_out, const int8_t *a
                        (crl_u64 *)stats, (long long)B, prm, flags
 #define TRON_STEP_LAUNCH(T)                                                                                         \
     do {                                                                                                          \
-        if (use_pdl) CRL_LAUNCH_PDL(tron_step_kernel<T>, blocks_for(B, T), T, (cudaStream_t)stream, TRON_STEP_ARGS);   \
-        else CRL_LAUNCH(tron_step_kernel<T>, blocks_for(B, T), T, (cudaStream_t)stream, TRON_STEP_ARGS);              \
+        CRL_LAUNCH_PDL(tron_step_kernel<T>, blocks_for(B, T), T, (cudaStream_t)stream, TRON_STEP_ARGS);             \
     } while (0)
     if (tile == 32) TRON_STEP_LAUNCH(32);
     else TRON_STEP_LAUNCH(64);
@@ -535,7 +483,7 @@ int crl_ttt_step(const void *state_in, void *state_out, const int8_t *actions, u
     if (rc) return rc;
     if (!state_in || !state_out || !actions || !result || B < 0) return fail(CRL_ERR_ARG, "crl_ttt_step: bad argument%s");
     if (B == 0) return CRL_OK;
-#define TTT_STEP(NP) CRL_LAUNCH(ttt_step_kernel<NP>, ttt_blocks(B), 256, (cudaStream_t)stream, (const uint4 *)state_in, \
+#define TTT_STEP(NP) CRL_LAUNCH_PDL(ttt_step_kernel<NP>, ttt_blocks(B), 256, (cudaStream_t)stream, (const uint4 *)state_in, \
                                (uint4 *)state_out, actions, (uint32_t *)result, valid_after, (crl_u64 *)stats, (long long)B, flags)
     if (n == 2) TTT_STEP(2); else if (n == 3) TTT_STEP(3); else TTT_STEP(4);
 #undef TTT_STEP
@@ -574,7 +522,7 @@ int crl_ttt_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed,
     if (!state || B < 0 || K < 0) return fail(CRL_ERR_ARG, "crl_ttt_rollout: bad argument%s");
     if (B == 0 || K == 0) return CRL_OK;
     const PhiloxKeys keys = philox_expand_keys((crl_u64)seed);
-#define TTT_ROLL(NP) CRL_LAUNCH(ttt_rollout_kernel<NP>, ttt_blocks(B), 256, (cudaStream_t)stream, (uint4 *)state, \
+#define TTT_ROLL(NP) CRL_LAUNCH_PDL(ttt_rollout_kernel<NP>, ttt_blocks(B), 256, (cudaStream_t)stream, (uint4 *)state, \
                                (uint32_t *)result, (crl_u64 *)stats, (long long)B, keys, (crl_u64)first_env, step0, K)
     if (n == 2) TTT_ROLL(2); else if (n == 3) TTT_ROLL(3); else TTT_ROLL(4);
 #undef TTT_ROLL

@@ -10,7 +10,12 @@
 // dynamic shared memory (sized at launch); the emulator gives it its maximum size statically
 #define CRL_DYN_SMEM(name, maxbytes) extern __shared__ __align__(128) uint8_t name[]
 // launch with the programmatic-stream-serialization attribute (PDL); the kernel must call pdl_wait() before it
-// touches memory written by its predecessor in the stream
+// touches memory written by its predecessor in the stream.  CRL_PDL=0 in the environment launches plainly (A/B runs).
+#include <stdlib.h>
+static inline bool crl_use_pdl() {
+    static const bool on = !(getenv("CRL_PDL") && atoi(getenv("CRL_PDL")) == 0);
+    return on;
+}
 #define CRL_LAUNCH_PDL(kernel, grid_, block_, stream_, ...)                                         \
     do {                                                                                          \
         cudaLaunchConfig_t cfg_ = {};                                                             \
@@ -19,7 +24,7 @@
         cudaLaunchAttribute at_[1];                                                               \
         at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                           \
         at_[0].val.programmaticStreamSerializationAllowed = 1;                                    \
-        cfg_.attrs = at_; cfg_.numAttrs = 1;                                                      \
+        cfg_.attrs = at_; cfg_.numAttrs = crl_use_pdl() ? 1 : 0;                                   \
         cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                           \
     } while (0)
 #else
@@ -137,6 +142,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, int x, int y
 __device__ __forceinline__ void tensormap_prefetch(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(tm) : "memory");
 }
+// L2 prefetch hints (no architectural effect): a 1-D range (multiple of 16 bytes, 16-byte aligned) / a 2-D tensor box
+__device__ __forceinline__ void l2_prefetch_bulk(const void *src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src_gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_tensor_2d(const CUtensorMap *tm, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(tm), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit_wait_read() {
@@ -145,6 +157,13 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
+
+// per-thread L2 prefetch hint of the 128-byte line that holds *p
+__device__ __forceinline__ void l2_prefetch_line(const void *p) {
+#ifndef CRL_HOSTSIM
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
 
 // ---- programmatic dependent launch (PDL): overlap a kernel's launch + prologue with its predecessor's tail ----
 __device__ __forceinline__ void pdl_launch_dependents() {

@@ -388,7 +388,24 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
     const int n = (int)min((long long)TILE, B - e0);
     const bool valid = t < n;
     const uint32_t lane_const = TRON_STAT_LANE[t & 31];
+    // PDL prologue: this runs while the predecessor in the stream is still executing.  Nothing may be READ yet, but the
+    // tile, its header and its actions can be pulled from HBM into L2 (prefetches are hints: if the predecessor is
+    // still writing these very lines, L2 already holds / will hold the coherent copy), so that the loads issued after
+    // griddepcontrol.wait are L2 hits and HBM keeps streaming across the launch boundary.
+#ifndef CRL_HOSTSIM
+    if (t == 0 && !(flags & 0x2000)) {
+        l2_prefetch_tensor_2d(&maps.in, (int)(e0 * 4), 0);
+        l2_prefetch_bulk(in + 12ll * B + e0, (uint32_t)(n * 16));
+        const uint32_t abytes = (uint32_t)((flags & CRL_FLAG_PACKED_ACTIONS) ? n : 4 * n);
+        const char *ap = (const char *)actions + ((flags & CRL_FLAG_PACKED_ACTIONS) ? e0 : 4 * e0);
+        if (!(abytes & 15u) && !((uintptr_t)ap & 15)) l2_prefetch_bulk(ap, abytes);
+    }
+#endif
     pdl_wait();                  // (programmatic dependent launch only) everything above overlapped the previous kernel's tail
+    // let the successor's CTAs become resident NOW: its prologue prefetch then overlaps this launch's own traffic.  The
+    // successor still blocks at its griddepcontrol.wait until this grid has completed, and ITS successor cannot start
+    // before it has passed that wait -- at most two launches are ever co-resident.
+    if (!(flags & 0x1000)) pdl_launch_dependents();
     uint32_t a = 0u;                                         // in flight together with the tile
     if (valid) {
         if (flags & CRL_FLAG_PACKED_ACTIONS) {               // one byte per environment, 2 bits per player
@@ -405,13 +422,14 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
     c.Z = c.W = 0u;
     tron_tile_wait(bar, 0);
     // flags >= 0x100 are diagnostics (tools/tron_probe.py): 0x100 data movement only, 0x200 no phase 2, 0x400 no
-    // phase 3, 0x800 no statistics -- results are meaningless with any of them
+    // phase 3, 0x800 no statistics -- results are meaningless with any of them; 0x1000 late PDL trigger, 0x2000 no
+    // prologue prefetch (results unaffected)
     const bool work = valid && !(flags & 0x100);
     if (work) tron_phase1<TILE>(c, tile.v[12][t], a, prm, (flags & CRL_FLAG_AUTO_RESET) != 0);
     tron_tile_wait(bar, 1);
     if (work && !(flags & 0x200)) tron_phase2(c, tile, t, prm);
     tron_tile_store(tile, &maps, out, B, e0, n, true, false);
-    pdl_launch_dependents();     // the next launch's CTAs may become resident while the planes drain
+    if (flags & 0x1000) pdl_launch_dependents();     // (diagnostic: the round-1 trigger position)
     if (work) {
         if (!(flags & 0x400)) tron_phase3(c, prm, o);
         tile.v[12][t] = tron_ctx_header(c);
@@ -426,108 +444,6 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
     // after the last store, so that the header is already draining (measured 0.1 us / step cheaper than before it)
     if (stats && !(flags & 0x800))
         tron_stats<crl_u64, crl_u64>(stats + (blockIdx.x & (CRL_STAT_ROWS - 1)) * CRL_NSTAT, valid, o, c.Z, c.W, lane_const);
-}
-
-// ---- persistent warp-worker variant (the default, see crl_tron_step) -----------------------------------------------
-// ONE CTA per SM (grid = min(#SMs, tiles)), NW warps per CTA, every warp an independent worker that owns a private
-// 32-environment tile slot in shared memory and walks the tiles  w * gridDim + blockIdx, + NW * gridDim, ... :
-//   lane 0: ONE 2-D TMA load of the [13 rows][32 envs x 16 B] box (planes + header, 6.5 KB) -> mbarrier wait ->
-//   phases 1-3 on the slot (warp-synchronous, no CTA barrier anywhere) -> fence.proxy.async -> ONE 2-D TMA store.
-// At the configured batch (65,536 envs = 2,048 tiles over 148 SMs x 16 warps) every worker gets at most one tile, so
-// the whole batch is in flight at once (92 KB per SM) and the kernel costs 148 CTA launches instead of 1,024; larger
-// batches loop, and the slot of a worker is re-armed as soon as its store has READ the slot (wait_group.read), i.e.
-// the drain of tile i overlaps the load of tile i + 1 of the same worker and everything of the 15 other workers.
-// PDL: barrier init / tensor-map prefetch / index arithmetic run before griddepcontrol.wait.
-#define TRON_WTILE 32
-template <int NW>
-__global__ void __launch_bounds__(32 * NW, 1)
-tron_step_warp_kernel(const __grid_constant__ TronMaps maps, const uint32_t *__restrict__ actions,
-                      uint2 *__restrict__ result, crl_u64 *stats, long long B, TronParams prm, int flags, int ntiles) {
-    CRL_DYN_SMEM(tron_smem_raw, NW * sizeof(TronTile<TRON_WTILE>));
-    __shared__ __align__(8) uint64_t bar[NW];
-    TronTile<TRON_WTILE> *tiles = reinterpret_cast<TronTile<TRON_WTILE> *>(tron_smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    TronTile<TRON_WTILE> &tile = tiles[warp];
-    const int total = NW * (int)gridDim.x;
-    const uint32_t lane_const = TRON_STAT_LANE[lane];
-#ifndef CRL_HOSTSIM
-    if (lane == 0) {
-        mbar_init(&bar[warp], 1);
-        tensormap_prefetch(&maps.in);
-        tensormap_prefetch(&maps.out);
-    }
-    __syncwarp();
-#endif
-    pdl_wait();
-    uint32_t phase = 0u;
-    bool triggered = false;
-    for (int tl = warp * (int)gridDim.x + (int)blockIdx.x; tl < ntiles; tl += total) {
-        const long long e0 = (long long)tl * TRON_WTILE;
-        const int n = (int)min((long long)TRON_WTILE, B - e0);
-        const bool valid = lane < n;
-#ifndef CRL_HOSTSIM
-        if (lane == 0) {
-            mbar_expect_tx(&bar[warp], (uint32_t)(TRON_VEC * TRON_WTILE * 16));   // clipped columns are zero-filled and count
-            tma_load_2d(&tile.v[0][0], &maps.in, (int)(e0 * 4), 0, &bar[warp]);
-        }
-#else
-        for (int v = 0; v < TRON_VEC; v++)
-            if (valid) tile.v[v][lane] = maps.in_ptr[(long long)v * B + e0 + lane];
-        __syncwarp();
-#endif
-        uint32_t a = 0u;                                         // in flight together with the tile
-        if (valid) {
-            if (flags & CRL_FLAG_PACKED_ACTIONS) {
-                const uint32_t b = ((const uint8_t *)actions)[e0 + lane];
-                a = (b & 3u) | (b & 0xcu) << 6 | (b & 0x30u) << 12 | (b & 0xc0u) << 18;
-            } else {
-                a = actions[e0 + lane];
-            }
-        }
-        TronOut o;
-        tron_zero_out(o);
-        TronCtx c;
-        c.Z = c.W = 0u;
-#ifndef CRL_HOSTSIM
-        mbar_wait(&bar[warp], phase);
-        phase ^= 1u;
-#endif
-        const bool work = valid && !(flags & 0x100);            // diagnostics as in tron_step_kernel
-        if (work) {
-            tron_phase1<TRON_WTILE>(c, tile.v[12][lane], a, prm, (flags & CRL_FLAG_AUTO_RESET) != 0);
-            if (!(flags & 0x200)) tron_phase2(c, tile, lane, prm);
-            if (!(flags & 0x400)) tron_phase3(c, prm, o);
-            tile.v[12][lane] = tron_ctx_header(c);
-        }
-#ifndef CRL_HOSTSIM
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            tma_store_2d(&maps.out, (int)(e0 * 4), 0, &tile.v[0][0]);
-            bulk_commit();
-        }
-#else
-        __syncwarp();
-        for (int v = 0; v < TRON_VEC; v++)
-            if (valid) maps.out_ptr[(long long)v * B + e0 + lane] = tile.v[v][lane];
-        __syncwarp();
-#endif
-        if (!triggered) { pdl_launch_dependents(); triggered = true; }
-        if (work) {
-            const uint2 rec = tron_pack_result(o);
-            if (flags & CRL_FLAG_COMPACT2_RESULT)
-                ((uint16_t *)result)[e0 + lane] = (uint16_t)(((rec.y >> 8) & 0xfu) | (rec.y & 1u) << 4 | (rec.y >> 24) << 8);
-            else if (flags & CRL_FLAG_COMPACT_RESULT) ((uint32_t *)result)[e0 + lane] = rec.y;
-            else result[e0 + lane] = rec;
-        }
-        if (stats && !(flags & 0x800))
-            tron_stats<crl_u64, crl_u64>(stats + (tl & (CRL_STAT_ROWS - 1)) * CRL_NSTAT, valid, o, c.Z, c.W, lane_const);
-#ifndef CRL_HOSTSIM
-        if (lane == 0) bulk_wait_read();                         // the slot may be re-armed once the store has read it
-        __syncwarp();
-#endif
-    }
-    if (!triggered) pdl_launch_dependents();
 }
 
 // K fused steps with the in-kernel Philox random policy (action of player p = {0,+1,-1}[r_p % 3]); the tile

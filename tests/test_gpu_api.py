@@ -193,8 +193,33 @@ def test_tron_new_state_spawn_arguments():
         (board, heads, dirs, deaths), players = single.new_state(ring_offset=ring, spawn_offset=spawn)
         assert heads.tolist() == row[5:9].tolist() and dirs.tolist() == row[9:13].tolist() and not deaths.any()
         assert board.ravel()[heads].tolist() == [1, 2, 3, 4] and int((board != 0).sum()) == 4
-    # the tuple form draws an offset in [lo, hi)
-    (board, heads, dirs, deaths), _ = single.new_state(spawn_offset=(-1, 2))
-    assert any(heads.tolist() == want[(15, 4, 1, s)][5:9].tolist() for s in (-1, 0, 1))
+    # the tuple form draws one offset in [lo, hi) PER PLAYER (:222-224)
+    for _ in range(8):
+        (board, heads, dirs, deaths), _ = single.new_state(spawn_offset=(-1, 2))
+        for p in range(4):
+            assert any(int(heads[p]) == int(want[(15, 4, 1, s)][5 + p]) and int(dirs[p]) == int(want[(15, 4, 1, s)][9 + p])
+                       for s in (-1, 0, 1))
+    # explicit per-player offsets: player p takes the spawn of the table row of ITS offset; auto-reset keeps them
+    offs = [2, -1, 0, 3]
+    h, d = env.generate_start_positions(1, offs)
+    assert h.tolist() == [int(want[(15, 4, 1, o)][5 + p]) for p, o in enumerate(offs)]
+    assert d.tolist() == [int(want[(15, 4, 1, o)][9 + p]) for p, o in enumerate(offs)]
+    renv = BatchedTronGridEnvironment("15;4", batch=64, auto_reset=True, seed=9)
+    state, _ = renv.new_state(ring_offset=1, spawn_offset=offs)
+    start = renv.state_to_observation(state, -1)
+    assert (start["heads"].cpu().numpy() == h[None]).all()
+    ended = np.zeros(64, bool)
+    for t in range(60):
+        state, _, _, terminal, _ = renv.next_state(state, None, renv.random_actions(t), out=state)
+        ended |= terminal.cpu().numpy().astype(bool)
+    assert ended.all()
+    # step once more with everything finished at some point: finished games restarted from THESE spawns
+    term = renv.is_terminal(state).cpu().numpy().astype(bool)
+    assert term.any()
+    state, *_ = renv.next_state(state, None, torch.zeros((64, 4), dtype=torch.int8), out=state)
+    obs = renv.state_to_observation(state, -1)
+    N = 15
+    step = np.array([-N, 1, N, -1])                                  # one forward move from the spawn, per direction
+    assert (obs["heads"].cpu().numpy()[term] == (h + step[d])[None]).all()
     with pytest.raises(Exception):
         env.new_state(ring_offset=9)                     # no such ring on a 15 x 15 board

@@ -16,8 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from colosseumrl_b200.tron import BatchedTronGridEnvironment  # noqa: E402
 
-VARIANTS = [("full", 0), ("no stats", 0x800), ("no phase3, no stats", 0xC00), ("no phase2/3, no stats", 0xE00),
-            ("data movement only", 0x100 | 0x800)]
+VARIANTS = [("full", 0), ("full, late PDL trigger", 0x1000), ("full, no L2 prefetch", 0x2000),
+            ("full, round-1 (late trigger, no prefetch)", 0x3000),
+            ("no stats", 0x800), ("no phase3, no stats", 0xC00), ("no phase2/3, no stats", 0xE00),
+            ("data movement only", 0x100 | 0x800), ("data movement only, round-1", 0x100 | 0x800 | 0x3000)]
 
 
 def main():
@@ -58,7 +60,7 @@ def main():
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) / K * 1e3)
         ts.sort()
-        print("%-26s min %.2f  median %.2f us/step   (%.0f GB/s algorithmic at min)" % (name, ts[0], ts[len(ts) // 2], 424 * B / ts[0] / 1e3))
+        print("%-44s min %.2f  median %.2f us/step   (%.0f GB/s algorithmic at min)" % (name, ts[0], ts[len(ts) // 2], 424 * B / ts[0] / 1e3))
 
 
 if __name__ == "__main__":
