@@ -392,6 +392,7 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
     // tile, its header and its actions can be pulled from HBM into L2 (prefetches are hints: if the predecessor is
     // still writing these very lines, L2 already holds / will hold the coherent copy), so that the loads issued after
     // griddepcontrol.wait are L2 hits and HBM keeps streaming across the launch boundary.
+    if (flags & 0x4000) pdl_launch_dependents();             // (diagnostic: trigger before the prefetch / wait)
 #ifndef CRL_HOSTSIM
     if (t == 0 && !(flags & 0x2000)) {
         l2_prefetch_tensor_2d(&maps.in, (int)(e0 * 4), 0);
@@ -405,7 +406,7 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
     // let the successor's CTAs become resident NOW: its prologue prefetch then overlaps this launch's own traffic.  The
     // successor still blocks at its griddepcontrol.wait until this grid has completed, and ITS successor cannot start
     // before it has passed that wait -- at most two launches are ever co-resident.
-    if (!(flags & 0x1000)) pdl_launch_dependents();
+    if (!(flags & 0x5000)) pdl_launch_dependents();
     uint32_t a = 0u;                                         // in flight together with the tile
     if (valid) {
         if (flags & CRL_FLAG_PACKED_ACTIONS) {               // one byte per environment, 2 bits per player

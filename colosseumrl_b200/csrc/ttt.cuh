@@ -170,9 +170,8 @@ ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int
     TTTStatAcc acc;
     acc.clear();
     const long long stride = (long long)gridDim.x * blockDim.x;
-    // PDL prologue (see tron_step_kernel): pull this thread's lines into L2 while the predecessor drains
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < B; e += stride)
-        if (!(threadIdx.x & 7)) { l2_prefetch_line(in + e); if (!(threadIdx.x & 127)) l2_prefetch_line(actions + e); }
+    // (PDL launch: the grid may become resident while its predecessor drains; an L2 prefetch prologue like Tron's was
+    // measured and dropped -- this kernel is issue-bound and the extra instructions cost more than the overlap buys)
     pdl_wait();
     pdl_launch_dependents();
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < B; e += stride) {
@@ -286,8 +285,6 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
     acc.clear();
     int pending = 0;                                     // env-steps accumulated since the last flush (block-uniform)
     const long long stride = (long long)gridDim.x * blockDim.x, first = (long long)blockIdx.x * blockDim.x;
-    for (long long e0 = first; e0 < B; e0 += stride)     // PDL prologue: this thread's lines -> L2 (see tron_step_kernel)
-        if (!(threadIdx.x & 7) && e0 + threadIdx.x < B) l2_prefetch_line(state + e0 + threadIdx.x);
     pdl_wait();
     pdl_launch_dependents();
     for (long long e0 = first; e0 < B; e0 += stride) {   // block-uniform trip count: the flushes are warp-collective
