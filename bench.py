@@ -585,6 +585,8 @@ def measure_b200(name, args, cx, with_cpu):
     del g0
     node_cap = 30000 // wl["launches"]
     R = max(1, min(int(math.ceil(args.min_ms / (K * est))), max(1, node_cap // K)))
+    if args.reps > 0:
+        R = args.reps                              # (profiling: the same R as a plain run, whatever the profiler's clock says)
     # for the report only: the same steps as ONE dependent chain (every launch waits for its predecessor)
     serial, Rs = None, 0
     if S > 1:
@@ -605,9 +607,15 @@ def measure_b200(name, args, cx, with_cpu):
     clocks.start()
     ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     wall0 = time.perf_counter()
+    if args.profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()                # ncu --profile-from-start off: only the timed region is profiled
     ev0.record(stream)
     graph.replay()
     ev1.record(stream)
+    if args.profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     # the only collective: own row-sum kernel (256 rows -> 32 slots) + one all-reduce of 256 B, stream-ordered behind
     # the steps and inside the timed region; the host does not block on it
     total_stats, work_h = work.stats_env.all_reduce_stats(async_op=True)
@@ -628,6 +636,9 @@ def measure_b200(name, args, cx, with_cpu):
     launch_ms = step_ms / wl["launches"]
 
     # ---- end to end through the public API with host buffers: K x Re steps (>= --min-ms)
+    if args.no_e2e:
+        work.e2e_step = lambda k_: 0
+        work.e2e_drain = lambda: None
     for j in range(3):
         work.e2e_step(k); k += 1
     work.e2e_drain()
@@ -798,6 +809,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--min-ms", type=float, default=50.0,
                     help="minimum length of every timed region; the K-step sequence is repeated to fill it")
+    ap.add_argument("--reps", type=int, default=0, help="force the number of repetitions R (profiling runs)")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the timed graph replay with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     ap.add_argument("--replicas", type=int, default=0, help="independent batch replicas per GPU (0 = enough for 4 x L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-stats", action="store_true", help="exploration: skip the fused episode statistics")

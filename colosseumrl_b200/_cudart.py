@@ -16,6 +16,8 @@ def rt():
         lib.cudaEventRecord.argtypes = [C.c_void_p, C.c_void_p]
         lib.cudaEventSynchronize.argtypes = [C.c_void_p]
         lib.cudaEventDestroy.argtypes = [C.c_void_p]
+        lib.cudaGetLastError.argtypes = []
+        lib.cudaGetLastError.restype = C.c_int
         for f in (lib.cudaGraphLaunch, lib.cudaGraphUpload, lib.cudaEventCreateWithFlags, lib.cudaEventRecord,
                   lib.cudaEventSynchronize, lib.cudaEventDestroy):
             f.restype = C.c_int

@@ -81,6 +81,14 @@ class HostStepper:
     def launch(self):
         """Enqueue H2D + step + D2H (one graph launch) on the stepper's stream; returns immediately."""
         rc = self._rt.cudaGraphLaunch(self._exec, self._stream_handle) or self._rt.cudaEventRecord(self._done, self._stream_handle)
+        if rc == 400:
+            # cudaErrorInvalidResourceHandle: the calling thread's current device is not the stepper's.  The hot loop of a
+            # one-process-per-GPU actor never pays for a device guard; a multi-device process lands here and retries
+            # under one (the failed call launched nothing).
+            self._rt.cudaGetLastError()
+            with torch.cuda.device(self.env.device):
+                rc = self._rt.cudaGraphLaunch(self._exec, self._stream_handle) or \
+                    self._rt.cudaEventRecord(self._done, self._stream_handle)
         if rc:
             raise RuntimeError("HostStepper launch failed: cudaError %d" % rc)
 

@@ -222,7 +222,7 @@ def emit(path):
     L.append("//  .y = pieces that need s (own piece + descendants; 5-cell shapes are leaves) | parent's flag index << 24")
     L.append("//  .z = the shape's cells, 5 x 6 bits (dx | dy << 3), short shapes repeat cell 0")
     L.append("//  .w = byte offset of the shape's own row 4 (y = 0) | piece << 16 | cells << 24")
-    L.append("__device__ const uint4 BLK_SHAPE_TAB_G[BLK_NSHAPE + 5] = {")
+    L.append("__device__ const uint4 BLK_SHAPE_TAB_G[BLK_NSHAPE + 32] = {    // (padded: a pass reads entry s0 + lane with 32 lanes)")
     for i in range(len(shapes)):
         pc, cells = shapes[i]
         slot, flag = slot_flag(i)
@@ -239,7 +239,7 @@ def emit(path):
         y = need[i] | par << 24
         w = ((slot * FROWS + 4) * 4) | pc << 16 | len(cells) << 24
         L.append("    {0x%08xu, 0x%08xu, 0x%08xu, 0x%08xu}," % (x, y, cw, w))
-    for _ in range(5):
+    for _ in range(32):
         L.append("    {0u, 0u, 0u, 0u},")
     L.append("};")
     open(path, "w").write("\n".join(L) + "\n")
