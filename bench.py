@@ -52,7 +52,7 @@ WORKLOADS = {
     "tron": dict(desc="Tron 4-player 19x19, 65,536 batched envs, random actions (BASELINE.json configs[1])",
                  B=65536, bytes=424, state=208, kernel="tron_step_kernel", launches=1, dtype="u32"),
     "blokus": dict(desc="Blokus 4-player 20x20, valid_actions + next_state over 16,384 batched games (BASELINE.json configs[2])",
-                   B=16384, bytes=2196, state=352, kernel="blokus_legal_kernel", launches=3, dtype="u32"),
+                   B=16384, bytes=2196, state=352, kernel="blokus_legal_kernel", launches=3, dtype="u32", game_len=68),
     "ttt4": dict(desc="Tic Tac Toe 4-player 3x3x3, 1,048,576 batched envs, random self-play (BASELINE.json configs[3])",
                  B=1 << 20, bytes=36, state=16, kernel="ttt_rollout_kernel", launches=1, dtype="u32"),
     "ttt2": dict(desc="Tic Tac Toe 2-player 3x3, single env, random self-play through next_state (BASELINE.json configs[0])",
@@ -388,6 +388,9 @@ class BlokusWL:
     def prepare(self, k0, n):
         pass
 
+    def step_replica(self, g):
+        self.step(g)
+
     def step(self, k, slot=None):
         g = k % self.G
         env, st = self.envs[g], self.states[g]
@@ -533,6 +536,17 @@ def measure_b200(name, args, cx, with_cpu):
         for e in work.envs:
             e.collect_stats = False
 
+    # Blokus: a step costs up to 2x more in the opening than in the end game (list lengths 116 .. 900 .. 13), and all games
+    # of a replica start together.  Steady-state self-play has games in every phase, so replica g is advanced by
+    # g/G of a typical game (68 steps) before anything is timed: the timed steps then cover all phases evenly at any
+    # --steps (without this, the driver's K = 20 would time the opening only).  Untimed; statistics are zeroed later.
+    desync = 0
+    if wl.get("game_len") and not args.no_desync:
+        for g_ in range(G):
+            for _ in range(int(round(g_ * wl["game_len"] / G))):
+                work.step_replica(g_)
+                desync += 1
+        torch.cuda.synchronize()
     # warm-up: W eager launches through the public API as requested, plus enough to touch every replica once
     k = 0
     extra_warm = max(0, G - W)
@@ -697,7 +711,8 @@ def measure_b200(name, args, cx, with_cpu):
                              "stepped round-robin, no flush kernel" % (G, G * per_replica / 1e6),
                        "launch": "R = %d repetitions of the K-step sequence captured in one CUDA graph" % R +
                                  ("" if S == 1 else ", the independent replicas spread over %d parallel chains (a replica's own steps stay ordered)" % S),
-                       "chains": S, "state_bytes_per_env": wl["state"], "warmup_extra_steps": extra_warm + K + K * Rs,
+                       "chains": S, "state_bytes_per_env": wl["state"], "warmup_extra_steps": extra_warm + K + K * Rs + desync,
+                       "phase_desync_steps": desync,
                        "timed_region_ms": dev_ms_max, "steps_ms": steps_ms_max,
                        "stats_allreduce_ms": dev_ms_max - steps_ms_max,
                        "parallelism": "env-sharded x%d, no data-path collective, 1 stats all-reduce inside the timed region" % world},
@@ -815,6 +830,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
     ap.add_argument("--replicas", type=int, default=0, help="independent batch replicas per GPU (0 = enough for 4 x L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-desync", action="store_true", help="exploration: all Blokus replicas start in the same game phase")
     ap.add_argument("--no-stats", action="store_true", help="exploration: skip the fused episode statistics")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (exploration only)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

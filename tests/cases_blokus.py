@@ -102,6 +102,47 @@ def case_golden_games(be):
         assert (op == g["obs_pieces"][m]).all() and (osc == g["obs_score"][m]).all()
 
 
+def _list_hashes(counts, ids):
+    """oracle/make_golden_wide.py::list_hash of every row's first counts[i] ids."""
+    out = np.zeros(len(counts), np.uint64)
+    with np.errstate(over="ignore"):
+        pw = np.cumprod(np.full(ids.shape[1], np.uint64(0x9E3779B97F4A7C15), np.uint64))
+        for i, n in enumerate(counts):
+            out[i] = ((ids[i, :n].astype(np.int64) + 1).astype(np.uint64) * pw[:n]).sum(dtype=np.uint64)
+    return out
+
+
+def _check_wide(be, g, pre, board, inv, scores, rounds):
+    st = blk_pack(be, board, inv, scores, rounds, g[pre + "mover"])
+    counts, ids = blk_legal(be, st, cap=2048)
+    assert (counts == g[pre + "n_valid"]).all()
+    assert (_list_hashes(counts, ids) == g[pre + "valid_hash"]).all()
+    out, r = blk_step(be, st, g[pre + "action"])
+    b2, p2, s2, m2 = blk_unpack(be, out)
+    assert (b2 == g[pre + "board"]).all() and (p2 == g[pre + "inventory"]).all() and (s2 == g[pre + "scores"]).all()
+    assert (m2[:, 0] == g[pre + "round"]).all() and (m2[:, 1] == g[pre + "next_mover"]).all()
+    assert (m2[:, 2] == g[pre + "terminal"]).all()
+    assert (r["reward"] == g[pre + "reward"]).all() and (r["terminal"] == g[pre + "terminal"]).all()
+    assert (r["winners"] == g[pre + "winners"]).all() and (r["next_mover"] == g[pre + "next_mover"]).all()
+    assert not r["error"].any() and (r["placed"] == (g[pre + "action"] >= 0)).all()
+    assert (r["ranking"][r["terminal"]] == (0xf & ~r["winners"][r["terminal"]])).all()
+    # is_valid_action of the recorded (legal) action
+    placed = g[pre + "action"] >= 0
+    assert blk_is_valid(be, st, g[pre + "action"])[placed].all()
+
+
+def case_wide_golden(be, stride=1):
+    """tests/golden/blokus_wide.npz (oracle/make_golden_wide.py): 64 more reference games (valid lists through length
+    + order-sensitive hash) and the hand-built end-game positions (last-piece bonuses, tied winners)."""
+    g = np.load(os.path.join(GOLDEN, "blokus_wide.npz"))
+    gg = {k: g[k][::stride] if k.startswith("g_") else g[k] for k in g.files}
+    gfull = {"t": g["g_t"], "board": g["g_board"], "inventory": g["g_inventory"], "scores": g["g_scores"], "round": g["g_round"]}
+    board, inv, scores, rounds = (x[::stride] for x in _golden_prev(gfull))
+    _check_wide(be, gg, "g_", board, inv, scores, rounds)
+    e = {k: g[k][::stride] if k.startswith("e_") else g[k] for k in g.files}
+    _check_wide(be, e, "e_", e["e_i_board"], e["e_i_inventory"], e["e_i_scores"], e["e_i_round"])
+
+
 def case_illegal_actions(be):
     """Ids outside the mover's valid list are flagged and applied as a pass (engine contract)."""
     g = np.load(os.path.join(GOLDEN, "blokus_games.npz"))

@@ -36,3 +36,7 @@ def test_many_anchors(be):
 
 def test_is_valid(be):
     cases.case_is_valid(be, stride=6)
+
+
+def test_wide_golden(be):
+    cases.case_wide_golden(be, stride=9)

@@ -31,11 +31,11 @@ def num(x):
 def launches(src, dst):
     rows = [r for r in csv.reader(open(src)) if len(r) > 5]
     hdr = rows[0]
-    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    ki, vi, ui, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Metric Name")
     agg, order = {}, []
     for r in rows[1:]:
         v = num(r[vi])
-        if v is None:
+        if v is None or r[mi] != "gpu__time_duration.sum":
             continue
         if r[ui] == "ns":
             v /= 1e3
