@@ -489,6 +489,14 @@ class Ctx:
         if self.world > 1:
             self.dist.barrier()
 
+    def gather(self, value):
+        """One float per rank -> list over ranks (every rank gets it)."""
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device=self.dev)
+        t[self.rank] = value
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return [float(x) for x in t.tolist()]
+
     def max_over_ranks(self, values):
         t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
         if self.world > 1:
@@ -644,6 +652,7 @@ def measure_b200(name, args, cx, with_cpu):
     steps_ms = ev0.elapsed_time(ev1)
     dev_ms = ev0.elapsed_time(ev2)
     dev_ms_max, steps_ms_max = cx.max_over_ranks([dev_ms, steps_ms])
+    per_rank_step_ms = [x / (K * R) for x in cx.gather(steps_ms)]      # which GPU sets the max (B200s differ by a few % in HBM speed)
     ms_per_step = dev_ms_max / n_timed
     value = world * B * n_timed / (dev_ms_max * 1e-3)
     step_ms = steps_ms_max / n_timed
@@ -715,6 +724,7 @@ def measure_b200(name, args, cx, with_cpu):
                        "phase_desync_steps": desync,
                        "timed_region_ms": dev_ms_max, "steps_ms": steps_ms_max,
                        "stats_allreduce_ms": dev_ms_max - steps_ms_max,
+                       "per_rank_ms_per_step": per_rank_step_ms,
                        "parallelism": "env-sharded x%d, no data-path collective, 1 stats all-reduce inside the timed region" % world},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": work.h2d,
