@@ -27,6 +27,9 @@ SIGNATURES = {
     "crl_philox_words": (_int, [_vp, _u64, _u64, _u32, _u32, _i64, _vp]),
     "crl_stats_reduce": (_int, [_vp, _vp, _int, _vp]),
     "crl_tron_state_bytes": (_i64, [_int, _int, _i64]),
+    "crl_tron_action_stride": (_int, [_int, _int]),
+    "crl_tron_result_bytes": (_int, [_int, _int]),
+    "crl_tron_policy_random_wide": (_int, [_vp, _u64, _u64, _u32, _i64, _vp]),
     "crl_tron_start_positions": (_int, [_int, _int, C.POINTER(_i32), C.POINTER(_i32)]),
     "crl_tron_reset": (_int, [_vp, _vp, _i64, _int, _int, _vp]),
     "crl_tron_start_positions_at": (_int, [_int, _int, _int, _int, C.POINTER(_i32), C.POINTER(_i32)]),

@@ -6,6 +6,7 @@
 #include "crl_common.cuh"
 #include "philox.cuh"
 #include "tron.cuh"
+#include "tron_wide.cuh"
 #include "ttt.cuh"
 #include "blokus.cuh"
 #include "../../include/colosseum_b200.h"
@@ -74,11 +75,15 @@ int crl_stats_reduce(const int64_t *stats_rows, int64_t *out, int accumulate, cr
 /* ------------------------------------------------------------------------------------------- Tron */
 
 static int tron_check(int N, int P, int64_t B) {
-    if (N < 5 || N * N > 64 * TRON_WORDS || N > 255) return fail(CRL_ERR_UNSUPPORTED, "tron: board size must satisfy 5 <= N <= 19%s");
-    if (P < 2 || P > 4) return fail(CRL_ERR_UNSUPPORTED, "tron: player count must satisfy 2 <= P <= 4%s");
+    if (N < 5 || N > 64) return fail(CRL_ERR_UNSUPPORTED, "tron: board size must satisfy 5 <= N <= 64%s");
+    if (P < 2 || P > TRONW_MAXP) return fail(CRL_ERR_UNSUPPORTED, "tron: player count must satisfy 2 <= P <= 8%s");
     if (B < 0) return fail(CRL_ERR_ARG, "tron: negative batch%s");
     return CRL_OK;
 }
+
+// N <= 19 and P <= 4 (BASELINE.json's shape and everything near it) run the tuned kernels of tron.cuh on the 208-byte
+// layout; every other shape the reference accepts runs the plain kernels of tron_wide.cuh on the word-major layout.
+static inline bool tron_wide(int N, int P) { return N * N > 64 * TRON_WORDS || P > 4; }
 
 // generate_start_positions (TronGridEnvironment.py:183-226); new_state's defaults are ring_offset = 1 and the
 // deterministic spawn_offset = 2 (:228, :222-224: randint(o, o + 1) == o).  The ring `ring_offset` cells in from the
@@ -131,7 +136,7 @@ static int tron_starts(int N, int P, int ring_offset, const int *spawn_offsets, 
     return CRL_OK;
 }
 
-static const int TRON_DEFAULT_SPAWNS[4] = {2, 2, 2, 2};           // new_state's default spawn_offset = 2 (:228)
+static const int TRON_DEFAULT_SPAWNS[TRONW_MAXP] = {2, 2, 2, 2, 2, 2, 2, 2};           // new_state's default spawn_offset = 2 (:228)
 
 // TronParams of (N, P, ring_offset, per-player spawn offsets); the last few are cached per thread -- every API call
 // needs them and tron_starts walks the whole ring.
@@ -140,6 +145,7 @@ static int tron_params(int N, int P, TronParams &prm, int ring_offset = 1, const
     struct Entry { int N, P, ring, so[4]; bool ok; TronParams prm; };
     static thread_local Entry cache[4];
     static thread_local int next = 0;
+    if (tron_wide(N, P)) return fail(CRL_ERR_UNSUPPORTED, "tron: internal error (wide shape on the packed path)%s");
     for (int i = 0; i < 4; i++) {
         const Entry &e = cache[i];
         if (e.ok && e.N == N && e.P == P && e.ring == ring_offset && e.so[0] == spawn_offsets[0] && e.so[1] == spawn_offsets[1] &&
@@ -171,6 +177,29 @@ static int tron_params_build(int N, int P, TronParams &prm, int ring_offset, con
     h.terminal = 0; h.ep_len = 0;
     uint4 e = tron_hdr_encode(h);
     prm.start_hdr[0] = e.x; prm.start_hdr[1] = e.y; prm.start_hdr[2] = e.z; prm.start_hdr[3] = e.w;
+    return CRL_OK;
+}
+
+// the same for the wide layout (tron_wide.cuh)
+static int tron_wide_params(int N, int P, TronWideParams &prm, int ring_offset = 1, const int *spawn_offsets = TRON_DEFAULT_SPAWNS) {
+    struct Entry { int N, P, ring, so[TRONW_MAXP]; bool ok; TronWideParams prm; };
+    static thread_local Entry cache[4];
+    static thread_local int next = 0;
+    for (int i = 0; i < 4; i++) {
+        const Entry &e = cache[i];
+        bool same = e.ok && e.N == N && e.P == P && e.ring == ring_offset;
+        for (int p = 0; same && p < P; p++) same = e.so[p] == spawn_offsets[p];
+        if (same) { prm = e.prm; return CRL_OK; }
+    }
+    int32_t heads[TRONW_MAXP] = {0}, dirs[TRONW_MAXP] = {0};
+    if (tron_starts(N, P, ring_offset, spawn_offsets, heads, dirs) != CRL_OK)
+        return fail(CRL_ERR_ARG, "tron: cannot place spawns for this N / P / ring_offset / spawn_offset%s");
+    prm.N = N; prm.P = P; prm.WPP = (N * N + 31) / 32; prm.W = P * prm.WPP + 2 * P + 1;
+    for (int p = 0; p < TRONW_MAXP; p++) { prm.start_head[p] = p < P ? heads[p] : 0; prm.start_dir[p] = p < P ? dirs[p] : 0; }
+    Entry &e = cache[next];
+    e.N = N; e.P = P; e.ring = ring_offset; e.ok = true; e.prm = prm;
+    for (int p = 0; p < TRONW_MAXP; p++) e.so[p] = p < P ? spawn_offsets[p] : 0;
+    next = (next + 1) & 3;
     return CRL_OK;
 }
 
@@ -224,19 +253,30 @@ static int tron_tile() {
 
 int64_t crl_tron_state_bytes(int N, int P, int64_t B) {
     if (tron_check(N, P, B)) return -1;
+    if (tron_wide(N, P)) return (int64_t)(P * ((N * N + 31) / 32) + 2 * P + 1) * 4 * B;
     return (int64_t)TRON_VEC * 16 * B;
+}
+
+int crl_tron_action_stride(int N, int P) {
+    if (tron_check(N, P, 0)) return -1;
+    return tron_wide(N, P) ? TRONW_MAXP : 4;
+}
+
+int crl_tron_result_bytes(int N, int P) {
+    if (tron_check(N, P, 0)) return -1;
+    return tron_wide(N, P) ? 16 : 8;
 }
 
 // per-player spawn offsets -> the fixed-size array the helpers take (absent players: 0)
 static int tron_spawn_array(int P, const int32_t *spawn_offsets, int *so) {
     if (!spawn_offsets) return fail(CRL_ERR_ARG, "tron: null spawn_offsets%s");
-    for (int p = 0; p < 4; p++) so[p] = p < P ? (int)spawn_offsets[p] : 0;
+    for (int p = 0; p < TRONW_MAXP; p++) so[p] = p < P ? (int)spawn_offsets[p] : 0;
     return CRL_OK;
 }
 
 int crl_tron_start_positions_spawns(int N, int P, int ring_offset, const int32_t *spawn_offsets, int32_t *heads,
                                     int32_t *directions) {
-    int rc = tron_check(N, P, 0), so[4];
+    int rc = tron_check(N, P, 0), so[TRONW_MAXP];
     if (rc) return rc;
     if (!heads || !directions) return fail(CRL_ERR_ARG, "crl_tron_start_positions: null pointer%s");
     if ((rc = tron_spawn_array(P, spawn_offsets, so))) return rc;
@@ -246,7 +286,8 @@ int crl_tron_start_positions_spawns(int N, int P, int ring_offset, const int32_t
 }
 
 int crl_tron_start_positions_at(int N, int P, int ring_offset, int spawn_offset, int32_t *heads, int32_t *directions) {
-    const int32_t so[4] = {spawn_offset, spawn_offset, spawn_offset, spawn_offset};
+    int32_t so[TRONW_MAXP];
+    for (int p = 0; p < TRONW_MAXP; p++) so[p] = spawn_offset;
     return crl_tron_start_positions_spawns(N, P, ring_offset, so, heads, directions);
 }
 
@@ -256,10 +297,17 @@ int crl_tron_start_positions(int N, int P, int32_t *heads, int32_t *directions) 
 
 int crl_tron_reset_spawns(void *state, const uint8_t *mask, int64_t B, int N, int P, int ring_offset,
                           const int32_t *spawn_offsets, crl_stream_t stream) {
-    int rc = tron_check(N, P, B), so[4];
+    int rc = tron_check(N, P, B), so[TRONW_MAXP];
     if (rc) return rc;
     if (!state) return fail(CRL_ERR_ARG, "crl_tron_reset: null state%s");
     if ((rc = tron_spawn_array(P, spawn_offsets, so))) return rc;
+    if (tron_wide(N, P)) {
+        TronWideParams wp;
+        if ((rc = tron_wide_params(N, P, wp, ring_offset, so))) return rc;
+        if (B == 0) return CRL_OK;
+        CRL_LAUNCH(tronw_reset_kernel, blocks_for(B * wp.W, 256), 256, (cudaStream_t)stream, (uint32_t *)state, mask, (long long)B, wp);
+        return check_launch("tronw_reset_kernel");
+    }
     TronParams prm;
     if ((rc = tron_params(N, P, prm, ring_offset, so))) return rc;
     if (B == 0) return CRL_OK;
@@ -269,7 +317,8 @@ int crl_tron_reset_spawns(void *state, const uint8_t *mask, int64_t B, int N, in
 
 int crl_tron_reset_at(void *state, const uint8_t *mask, int64_t B, int N, int P, int ring_offset, int spawn_offset,
                       crl_stream_t stream) {
-    const int32_t so[4] = {spawn_offset, spawn_offset, spawn_offset, spawn_offset};
+    int32_t so[TRONW_MAXP];
+    for (int p = 0; p < TRONW_MAXP; p++) so[p] = spawn_offset;
     return crl_tron_reset_spawns(state, mask, B, N, P, ring_offset, so, stream);
 }
 
@@ -288,7 +337,7 @@ int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, 
 int crl_tron_step_spawns(const void *state_in, void *state_out, const int8_t *actions, uint8_t *result, int64_t *stats,
                          int64_t B, int N, int P, int flags, int ring_offset, const int32_t *spawn_offsets,
                          crl_stream_t stream) {
-    int rc = tron_check(N, P, B), so[4];
+    int rc = tron_check(N, P, B), so[TRONW_MAXP];
     if (rc) return rc;
     if ((rc = tron_spawn_array(P, spawn_offsets, so))) return rc;
     return tron_step_impl(state_in, state_out, actions, result, stats, B, N, P, flags, ring_offset, so, stream);
@@ -302,6 +351,17 @@ static int tron_step_impl(const void *state_in, void *state_out, const int8_t *a
     int rc = tron_check(N, P, B);
     if (rc) return rc;
     if (!state_in || !state_out || !actions || !result) return fail(CRL_ERR_ARG, "crl_tron_step: null pointer%s");
+    if (tron_wide(N, P)) {
+        if (flags & (CRL_FLAG_COMPACT_RESULT | CRL_FLAG_COMPACT2_RESULT | CRL_FLAG_PACKED_ACTIONS))
+            return fail(CRL_ERR_UNSUPPORTED, "crl_tron_step: compact records / packed actions exist for N <= 19, P <= 4 only%s");
+        TronWideParams wp;
+        if ((rc = tron_wide_params(N, P, wp, ring_offset, so))) return rc;
+        if (B == 0) return CRL_OK;
+        if (((uintptr_t)actions & 7) || ((uintptr_t)result & 15)) return fail(CRL_ERR_ARG, "crl_tron_step: actions must be 8-byte, result 16-byte aligned%s");
+        CRL_LAUNCH(tronw_step_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (const uint32_t *)state_in, (uint32_t *)state_out,
+                   actions, (uint4 *)result, (crl_u64 *)stats, (long long)B, wp, flags);
+        return check_launch("tronw_step_kernel");
+    }
     TronParams prm;
     if ((rc = tron_params(N, P, prm, ring_offset, so))) return rc;
     if (B == 0) return CRL_OK;
@@ -342,11 +402,28 @@ int crl_tron_policy_random(int8_t *actions, uint64_t seed, uint64_t first_env, u
     return check_launch("tron_policy_random_kernel");
 }
 
+int crl_tron_policy_random_wide(int8_t *actions, uint64_t seed, uint64_t first_env, uint32_t step, int64_t B,
+                                crl_stream_t stream) {
+    if (!actions || B < 0 || ((uintptr_t)actions & 7)) return fail(CRL_ERR_ARG, "crl_tron_policy_random_wide: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(tronw_policy_random_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, actions, (long long)B,
+               (crl_u64)seed, (crl_u64)first_env, step);
+    return check_launch("tronw_policy_random_kernel");
+}
+
 int crl_tron_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed, uint64_t first_env,
                      uint32_t step0, int K, int64_t B, int N, int P, crl_stream_t stream) {
     int rc = tron_check(N, P, B);
     if (rc) return rc;
     if (!state || K < 0) return fail(CRL_ERR_ARG, "crl_tron_rollout: bad argument%s");
+    if (tron_wide(N, P)) {
+        TronWideParams wp;
+        if ((rc = tron_wide_params(N, P, wp))) return rc;
+        if (B == 0 || K == 0) return CRL_OK;
+        CRL_LAUNCH(tronw_rollout_kernel, blocks_for(B, 128), 128, (cudaStream_t)stream, (uint32_t *)state, (uint4 *)result,
+                   (crl_u64 *)stats, (long long)B, wp, (crl_u64)seed, (crl_u64)first_env, step0, K);
+        return check_launch("tronw_rollout_kernel");
+    }
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0 || K == 0) return CRL_OK;
@@ -364,6 +441,15 @@ int crl_tron_observe(const void *state, int player, int8_t *board, int32_t *head
     int rc = tron_check(N, P, B);
     if (rc) return rc;
     if (!state || !board || player >= P || player < -3 || player == -2) return fail(CRL_ERR_ARG, "crl_tron_observe: bad argument%s");
+    if (tron_wide(N, P)) {
+        TronWideParams wp;
+        if ((rc = tron_wide_params(N, P, wp))) return rc;
+        if (B == 0) return CRL_OK;
+        const int64_t n = B * (player == -3 ? P : 1) * N * N;
+        CRL_LAUNCH(tronw_observe_kernel, blocks_for(n, 256), 256, (cudaStream_t)stream, (const uint32_t *)state, (long long)B, wp,
+                   player, board, heads, directions, deaths, terminal);
+        return check_launch("tronw_observe_kernel");
+    }
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
@@ -381,6 +467,15 @@ int crl_tron_ranking(const void *state, uint8_t *ranking, int64_t B, int N, int 
     int rc = tron_check(N, P, B);
     if (rc) return rc;
     if (!state || !ranking) return fail(CRL_ERR_ARG, "crl_tron_ranking: null pointer%s");
+    if (tron_wide(N, P)) {                                   // uint32 per environment, 3 bits per player
+        TronWideParams wp;
+        if ((rc = tron_wide_params(N, P, wp))) return rc;
+        if (B == 0) return CRL_OK;
+        if ((uintptr_t)ranking & 3) return fail(CRL_ERR_ARG, "crl_tron_ranking: ranking must be 4-byte aligned for wide shapes%s");
+        CRL_LAUNCH(tronw_ranking_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, (const uint32_t *)state, (long long)B, wp,
+                   (uint32_t *)ranking);
+        return check_launch("tronw_ranking_kernel");
+    }
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;
@@ -393,6 +488,14 @@ int crl_tron_pack(void *state, const int8_t *board, const int32_t *heads, const 
     int rc = tron_check(N, P, B);
     if (rc) return rc;
     if (!state || !board || !heads || !directions || !deaths) return fail(CRL_ERR_ARG, "crl_tron_pack: null pointer%s");
+    if (tron_wide(N, P)) {
+        TronWideParams wp;
+        if ((rc = tron_wide_params(N, P, wp))) return rc;
+        if (B == 0) return CRL_OK;
+        CRL_LAUNCH(tronw_pack_kernel, blocks_for(B * wp.W, 256), 256, (cudaStream_t)stream, (uint32_t *)state, (long long)B, wp,
+                   board, heads, directions, deaths);
+        return check_launch("tronw_pack_kernel");
+    }
     TronParams prm;
     if ((rc = tron_params(N, P, prm))) return rc;
     if (B == 0) return CRL_OK;

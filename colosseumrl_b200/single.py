@@ -115,14 +115,15 @@ class TronGridEnvironment(SingleEnvironment):
     def next_state(self, state, players: List[int], actions: List[str]):
         for player, action in zip(players, actions):
             self._moves[player] = self.STRING_TO_ACTION[action]  # unknown string: KeyError, as in the reference (:298)
-        act = torch.zeros((1, 4), dtype=torch.int8)
+        act = torch.zeros((1, self._b.action_stride), dtype=torch.int8)
         act[0, :self.num_players] = torch.from_numpy(self._moves.astype(np.int8))
         new = self._b.step_(self._pack(state), act)
         r = self._np(new.result[0])
         P = self.num_players
         rewards = r[:P].view(np.int8).astype(np.int64)
-        new_players = np.array([p for p in range(P) if r[5] >> p & 1], dtype=np.int64)
-        terminal = bool(r[4])
+        alive, term = (r[9], r[8]) if self._b.wide else (r[5], r[4])          # 16-byte record beyond N <= 19, P <= 4
+        new_players = np.array([p for p in range(P) if alive >> p & 1], dtype=np.int64)
+        terminal = bool(term)
         winners = new_players if terminal else None
         return self._unpack(new), new_players, rewards, terminal, winners
 

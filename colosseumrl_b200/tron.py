@@ -35,7 +35,8 @@ def parse_tron_config(config: str):
 @dataclass
 class TronBatchState:
     packed: torch.Tensor                    # int32 [13, B, 4]: SoA of 16-byte vectors, 208 B per environment
-    result: Optional[torch.Tensor] = None   # uint8 [B, 8] written by the step that produced this state
+    #                                         (shapes beyond N <= 19, P <= 4: int32 [W, B], csrc/tron_wide.cuh)
+    result: Optional[torch.Tensor] = None   # uint8 [B, 8] (wide shapes: [B, 16]) written by the step that produced this state
 
 
 class BatchedTronGridEnvironment(BatchedBaseEnvironment):
@@ -49,6 +50,11 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         self.N, self.num_players, self.observation_window, self.remove_on_death = parse_tron_config(config)
         if self._lib.crl_tron_state_bytes(self.N, self.num_players, self.batch) < 0:
             raise _lib.CrlError(self._lib.crl_last_error().decode())
+        # buffer geometry of this shape: 4 actions / 8 result bytes per environment on the tuned path (N <= 19, P <= 4),
+        # 8 / 16 on the wide path (include/colosseum_b200.h)
+        self.action_stride = self._lib.crl_tron_action_stride(self.N, self.num_players)
+        self.result_bytes = self._lib.crl_tron_result_bytes(self.N, self.num_players)
+        self.wide = self.action_stride != 4
         # the spawns of the last new_state(): auto-reset inside the step restarts finished games from the same ones
         self._ring_offset, self._spawn_offsets = 1, None          # None = the reference's defaults (1, 2)
 
@@ -80,6 +86,9 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
                 "deaths": (self.num_players,)}
 
     def _alloc(self):
+        if self.wide:
+            words = self._lib.crl_tron_state_bytes(self.N, self.num_players, 1) // 4
+            return torch.empty((words, self.batch), dtype=torch.int32, device=self.device)
         return torch.empty((13, self.batch, 4), dtype=torch.int32, device=self.device)
 
     def _spawn_array(self, spawn_offset):
@@ -120,7 +129,7 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         """generate_start_positions (:183-226): (heads = y * N + x, directions) as int64 numpy arrays."""
         import ctypes as C
         import numpy as np
-        h, d = (C.c_int32 * 4)(), (C.c_int32 * 4)()
+        h, d = (C.c_int32 * 8)(), (C.c_int32 * 8)()
         self._check(self._lib.crl_tron_start_positions_spawns(self.N, self.num_players, int(ring_offset),
                                                               self._spawn_array(spawn_offset), h, d))
         return (np.array(h[:self.num_players], np.int64), np.array(d[:self.num_players], np.int64))
@@ -147,21 +156,23 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
                                               self._stream)
 
     def next_state(self, state: TronBatchState, players, actions, out: Optional[TronBatchState] = None):
-        """TronGridEnvironment.next_state (:265-323).  actions: int8 [B, 4] (0 forward, 1 right, -1 left; entries of
-        dead players ignored).  `players` is accepted for signature parity and ignored (dense action tensor).
+        """TronGridEnvironment.next_state (:265-323).  actions: int8 [B, 4] ([B, 8] for shapes beyond N <= 19, P <= 4:
+        `self.action_stride`) (0 forward, 1 right, -1 left; entries of dead / absent players ignored).  `players` is accepted for signature parity and ignored (dense action tensor).
         Returns (new_state, new_players mask, rewards int8 [B, P], terminal uint8 [B], winners mask uint8 [B])."""
         new = self.step_(state, actions, out)
         r = new.result
+        if self.wide:                           # 16-byte record: reward[8] | terminal | alive | winners | 0 | ranking u32
+            return new, r[:, 9], r[:, :self.num_players].view(torch.int8), r[:, 8], r[:, 10]
         return new, r[:, 5], r[:, :self.num_players].view(torch.int8), r[:, 4], r[:, 6]
 
     def step_(self, state: TronBatchState, actions, out: Optional[TronBatchState] = None) -> TronBatchState:
         """The bare crl_tron_step launch (out may be `state` itself: in place).  Outputs are in new.result."""
         actions = self._dev(actions, torch.int8)
-        if actions.shape != (self.batch, 4):
-            raise ValueError("actions must have shape [B, 4]")
+        if actions.shape != (self.batch, self.action_stride):
+            raise ValueError("actions must have shape [B, %d]" % self.action_stride)
         new = out if out is not None else TronBatchState(self._alloc())
         if new.result is None:
-            new.result = self._new_result((self.batch, 8))
+            new.result = self._new_result((self.batch, self.result_bytes))
         self._check(self._step_call(state.packed.data_ptr(), new.packed.data_ptr(), actions.data_ptr(),
                                     new.result.data_ptr(), self.flags))
         return new
@@ -175,8 +186,10 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
         packed_actions=True: the pinned action buffer is uint8 [B], 2 bits per player (`pack_actions`), a quarter of
         the PCIe upload.  NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
         from .base import HostStepper
+        if self.wide and (compact or packed_actions):
+            raise ValueError("compact records / packed actions exist for N <= 19, P <= 4 only")
         if not compact and not packed_actions:
-            return HostStepper(self, state, (self.batch, 4), torch.int8, stream=stream)
+            return HostStepper(self, state, (self.batch, self.action_stride), torch.int8, stream=stream)
         width = 2 if compact == 2 else (4 if compact else 8)
         rec = torch.empty((self.batch, width), dtype=torch.uint8, device=self.device)
         flags = self.flags | {8: 0, 4: _lib.FLAG_COMPACT_RESULT, 2: _lib.FLAG_COMPACT2_RESULT}[width] | \
@@ -224,20 +237,23 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
 
     def is_terminal(self, state: TronBatchState) -> torch.Tensor:
         if state.result is not None:
-            return state.result[:, 4]
+            return state.result[:, 8 if self.wide else 4]
+        if self.wide:
+            return (state.packed[-1] & 1).to(torch.uint8)
         return ((state.packed[12, :, 2] >> 27) & 1).to(torch.uint8)
 
     def compute_ranking(self, state: TronBatchState, players=None, winners=None) -> torch.Tensor:
         """TronGridEnvironment.compute_ranking (:483-508), fused into the step: uint8 [B, P]."""
+        bits = 3 if self.wide else 2            # wide shapes: uint32 per environment, 3 bits per player
         if state.result is not None:
-            rk = state.result[:, 7].to(torch.int32)
+            rk = state.result[:, 12:16].contiguous().view(torch.int32)[:, 0] if self.wide else state.result[:, 7].to(torch.int32)
         else:                                   # a state that was not produced by a step (imported / fresh)
-            rk8 = torch.empty((self.batch,), dtype=torch.uint8, device=self.device)
-            self._check(self._lib.crl_tron_ranking(state.packed.data_ptr(), rk8.data_ptr(), self.batch, self.N,
+            rkb = torch.empty((self.batch,), dtype=torch.int32 if self.wide else torch.uint8, device=self.device)
+            self._check(self._lib.crl_tron_ranking(state.packed.data_ptr(), rkb.data_ptr(), self.batch, self.N,
                                                    self.num_players, self._stream))
-            rk = rk8.to(torch.int32)
-        shifts = 2 * torch.arange(self.num_players, device=self.device)
-        return ((rk[:, None] >> shifts[None]) & 3).to(torch.uint8)
+            rk = rkb.to(torch.int32)
+        shifts = bits * torch.arange(self.num_players, device=self.device)
+        return ((rk[:, None] >> shifts[None]) & ((1 << bits) - 1)).to(torch.uint8)
 
     def state_to_observation(self, state: TronBatchState, player: int) -> Dict[str, torch.Tensor]:
         """TronGridEnvironment.state_to_observation (:363-405); player = -1 gives the absolute (unrotated) state,
@@ -261,15 +277,15 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
 
     # -- random policy / fused rollouts (benchmark + self-play helpers) -------------------------------
     def random_actions(self, step: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        out = out if out is not None else torch.empty((self.batch, 4), dtype=torch.int8, device=self.device)
-        self._check(self._lib.crl_tron_policy_random(out.data_ptr(), self.seed, self.first_env_id, int(step),
-                                                     self.batch, self._stream))
+        out = out if out is not None else torch.empty((self.batch, self.action_stride), dtype=torch.int8, device=self.device)
+        fn = self._lib.crl_tron_policy_random_wide if self.wide else self._lib.crl_tron_policy_random
+        self._check(fn(out.data_ptr(), self.seed, self.first_env_id, int(step), self.batch, self._stream))
         return out
 
     def rollout(self, state: TronBatchState, step0: int, K: int) -> TronBatchState:
         """K random-policy steps with auto-reset in one launch (state updated in place)."""
         if state.result is None:
-            state.result = self._new_result((self.batch, 8))
+            state.result = self._new_result((self.batch, self.result_bytes))
         self._check(self._lib.crl_tron_rollout(state.packed.data_ptr(), state.result.data_ptr(), self._stats_ptr,
                                                self.seed, self.first_env_id, int(step0), int(K), self.batch, self.N,
                                                self.num_players, self._stream))

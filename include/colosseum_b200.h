@@ -73,8 +73,17 @@ int crl_philox_words(uint32_t *out, uint64_t seed, uint64_t first_env, uint32_t 
 int crl_stats_reduce(const int64_t *stats_rows, int64_t *out, int accumulate, crl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------- Tron
- * Packed state: 208 bytes per environment, SoA [13][B] of 16-byte vectors (csrc/tron.cuh).
- * Supported: 5 <= N <= 19 (N*N <= 384), 2 <= P <= 4.
+ * Any shape the reference's config string can name within 5 <= N <= 64, 2 <= P <= 8 (TronGridEnvironment.py:28-58;
+ * CyTronGrid.pyx:8-9 takes N and P from the array shapes).  Two state layouts, chosen by the shape alone:
+ *  - N <= 19 and P <= 4 (BASELINE.json's 19x19 4-player and everything near it): the tuned path.  Packed state 208 bytes
+ *    per environment, SoA [13][B] of 16-byte vectors (csrc/tron.cuh); actions int8[B][4]; result 8 bytes.  Everything
+ *    below describes this path.
+ *  - every other shape: the "wide" path (csrc/tron_wide.cuh), same entry points and semantics.  Packed state uint32
+ *    [W][B], W = P * ceil(N*N/32) + 2P + 1 (crl_tron_state_bytes tells); actions int8[B][8]; result 16 bytes per
+ *    environment = int8 reward[8] | u8 terminal | u8 alive mask | u8 winners mask | u8 0 | u32 ranking (3 bits per
+ *    player); crl_tron_ranking writes uint32[B] (3 bits per player); the compact-record / packed-action flags are not
+ *    available; the per-seat statistics slots cover seats 0..3.  crl_tron_action_stride / crl_tron_result_bytes return
+ *    4 / 8 or 8 / 16 so that callers can size their buffers without knowing the rule.
  * actions: int8[B][4]  (0 forward, +1 right, -1 left; TronGridEnvironment.STRING_TO_ACTION :62-67),
  *          entries of dead / absent players are ignored.  With CRL_FLAG_PACKED_ACTIONS: uint8[B], player p's
  *          action in bits 2p..2p+1 as (action & 3), i.e. 0 forward, 1 right, 3 left -- a quarter of the PCIe bytes.
@@ -88,6 +97,10 @@ int crl_stats_reduce(const int64_t *stats_rows, int64_t *out, int accumulate, cr
  *          ranking.  Nothing is lost: the winners of a terminal step ARE its alive players (:316-319) and the rewards
  *          follow as above; the device -> host read of a host-side actor (the slowest leg of its step) halves again. */
 int64_t crl_tron_state_bytes(int N, int P, int64_t B);
+/* HOST functions: int8 actions per environment (4 or 8) and bytes of a result record (8 or 16) for this shape; -1 if
+ * the shape is unsupported.  (The reference's counterpart is the length P of its per-player lists.) */
+int crl_tron_action_stride(int N, int P);
+int crl_tron_result_bytes(int N, int P);
 /* HOST function. generate_start_positions (TronGridEnvironment.py:183-226) with new_state's defaults:
  * heads[p] = y*N + x, directions[p] in {0 N, 1 E, 2 S, 3 W}. */
 int crl_tron_start_positions(int N, int P, int32_t *heads, int32_t *directions);
@@ -119,6 +132,10 @@ int crl_tron_step(const void *state_in, void *state_out, const int8_t *actions, 
 /* uniform random policy: action of player p = {0,+1,-1}[philox(env, step, tag 1)[p] % 3] */
 int crl_tron_policy_random(int8_t *actions, uint64_t seed, uint64_t first_env, uint32_t step, int64_t B,
                            crl_stream_t stream);
+/* the same policy for the wide layout: actions int8[B][8]; players 4..7 use {0,+1,-1}[(philox(...)[p - 4] / 3) % 3]
+ * (one Philox call per environment and step) */
+int crl_tron_policy_random_wide(int8_t *actions, uint64_t seed, uint64_t first_env, uint32_t step, int64_t B,
+                                crl_stream_t stream);
 /* K fused random-policy steps with auto-reset, state kept in registers (identical to K x policy+step) */
 int crl_tron_rollout(void *state, uint8_t *result_or_null, int64_t *stats_or_null, uint64_t seed,
                      uint64_t first_env, uint32_t step0, int K, int64_t B, int N, int P, crl_stream_t stream);

@@ -7,7 +7,7 @@
  *
  * Policy (identical to csrc/policy.cuh):
  *   words r[0..3] = philox4x32_10(ctr = (env_lo, env_hi, t, tag), key = (seed_lo, seed_hi))
- *   Tron   (tag 1): action of player p = {0, +1, -1}[r[p] % 3]
+ *   Tron   (tag 1): action of player p = {0, +1, -1}[r[p] % 3]   (players 4..7: [(r[p - 4] / 3) % 3])
  *   Blokus (tag 2): the (r[0] % n)-th entry of the mover's valid list, pass if n == 0
  *   TTT    (tag 3): the (r[0] % n_empty)-th empty cell in C order, pass if none
  * Auto-reset: an environment whose previous step returned terminal is replaced by new_state()
@@ -105,7 +105,7 @@ static void tron_env(int64_t e, int64_t *loc, void *argp, void *scratch) {
         if (a->terminal[e]) { orc_tron_new_state(N, P, bd, hd, dr, de); a->terminal[e] = 0; a->ep_len[e] = 0; }
         uint32_t r[4]; env_words(a->seed, (uint64_t)(a->env0 + e), a->t0 + s, 1, r);
         int64_t act[8] = {0}, rew[8];
-        for (int p = 0; p < P && p < 4; p++) act[p] = MOVE[r[p] % 3];
+        for (int p = 0; p < P && p < 8; p++) act[p] = MOVE[(p < 4 ? r[p] : r[p - 4] / 3) % 3];   /* = oracle/make_golden.py */
         int alive, winners;
         int term = orc_tron_next_state(N, P, bd, hd, dr, de, act, rew, &alive, &winners);
         a->ep_len[e]++; loc[0]++;

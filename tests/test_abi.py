@@ -46,8 +46,12 @@ def test_argument_validation_is_host_side():
     from colosseumrl_b200 import _lib
     lib = _lib.load()
     assert lib.crl_tron_state_bytes(19, 4, 65536) == 208 * 65536
-    assert lib.crl_tron_state_bytes(25, 4, 1) < 0 and b"board size" in lib.crl_last_error()      # N > 19: unsupported
-    assert lib.crl_tron_state_bytes(19, 5, 1) < 0 and b"player count" in lib.crl_last_error()
+    assert lib.crl_tron_state_bytes(25, 4, 1) == (4 * 20 + 9) * 4                                # N > 19: the wide layout
+    assert lib.crl_tron_state_bytes(19, 5, 1) == (5 * 12 + 11) * 4                               # P > 4: the wide layout
+    assert lib.crl_tron_state_bytes(65, 4, 1) < 0 and b"board size" in lib.crl_last_error()
+    assert lib.crl_tron_state_bytes(19, 9, 1) < 0 and b"player count" in lib.crl_last_error()
+    assert (lib.crl_tron_action_stride(19, 4), lib.crl_tron_result_bytes(19, 4)) == (4, 8)
+    assert (lib.crl_tron_action_stride(21, 4), lib.crl_tron_result_bytes(11, 6)) == (8, 16)
     assert lib.crl_blokus_state_bytes(16384) == 352 * 16384
     h, d = (C.c_int32 * 4)(), (C.c_int32 * 4)()
     assert lib.crl_tron_start_positions(19, 4, h, d) == 0 and list(h) == [30, 226, 330, 134] and list(d) == [2, 3, 0, 1]

@@ -52,7 +52,48 @@ def test_tron_api_episode():
     assert (st2.packed[:12] == state.packed[:12]).all()
 
 
-def test_ttt_api():
+def test_tron_api_wide_shapes():
+    """Shapes beyond N <= 19, P <= 4 through the Python surface (csrc/tron_wide.cuh): next_state / is_terminal /
+    compute_ranking / state_to_observation / rollout vs the oracle."""
+    from colosseumrl_b200.tron import BatchedTronGridEnvironment
+    for config, N, P, B, seed in (("21;4", 21, 4, 65, 3), ("11;6", 11, 6, 130, 4)):
+        env = BatchedTronGridEnvironment(config, batch=B, seed=seed)
+        assert env.wide and env.action_stride == 8 and env.result_bytes == 16
+        state, players = env.new_state()
+        assert (players.cpu().numpy() == (1 << P) - 1).all()
+        ost = [orc.tron_new_state(N, P) for _ in range(B)]
+        for t in range(14):
+            acts = env.random_actions(t)
+            a = acts.cpu().numpy()
+            state, players, rewards, terminal, winners = env.next_state(state, players, acts)
+            rk = env.compute_ranking(state, None, winners).cpu().numpy()
+            obs = {p: env.state_to_observation(state, p) for p in (0, P - 1)}
+            for e in range(0, B, 8):
+                ost[e], alive, orew, oterm, owin = orc.tron_next_state(ost[e], a[e, :P])
+                assert alive == int(players[e]) and (orew == rewards[e].cpu().numpy()).all()
+                assert oterm == bool(terminal[e]) and owin == int(winners[e]) and bool(env.is_terminal(state)[e]) == oterm
+                assert (orc.tron_compute_ranking(ost[e]) == rk[e]).all()
+                for p in (0, P - 1):
+                    oo = orc.tron_observation(ost[e], p)
+                    for k in ("board", "heads", "directions", "deaths"):
+                        assert (oo[k] == obs[p][k][e].cpu().numpy()).all()
+        # ranking of a state that no step produced (crl_tron_ranking) == the fused one
+        fresh = env.state_from_arrays(*(env.state_to_observation(state, -1)[k] for k in ("board", "heads", "directions", "deaths")))
+        assert (env.compute_ranking(fresh).cpu().numpy() == rk).all() and (env.is_terminal(fresh) == env.is_terminal(state)).all()
+        # fused rollout with auto-reset and statistics == the oracle's rollout
+        env2 = BatchedTronGridEnvironment(config, batch=B, seed=seed, auto_reset=True)
+        st2, _ = env2.new_state()
+        env2.rollout(st2, 0, 50)
+        ob = orc.TronBatch(B, N, P)
+        ob.rollout(seed, 0, 0, 50, fresh=True)
+        o2 = env2.state_to_observation(st2, -1)
+        assert (o2["board"].cpu().numpy() == ob.board).all() and (o2["deaths"].cpu().numpy() == ob.deaths).all()
+        assert (env2.stats.cpu().numpy() == ob.stats).all()
+        with pytest.raises(ValueError):
+            env.host_stepper(state, compact=2)
+
+
+def test_ttt_api():"""
     from colosseumrl_b200.tictactoe import BatchedTicTacToe4PlayerEnv, BatchedTicTacToe2PlayerEnv
     B, seed = 300, 2
     env = BatchedTicTacToe4PlayerEnv(batch=B, seed=seed, auto_reset=True)

@@ -13,7 +13,8 @@ TRON_ACTION = {0: "forward", 1: "right", -1: "left"}
 
 def test_tron_episodes_through_strings():
     from colosseumrl_b200.single import TronGridEnvironment
-    for name, config in (("tron_N19_P4", ""), ("tron_N7_P3", "7;3"), ("tron_N8_P2", "8;2")):
+    for name, config in (("tron_N19_P4", ""), ("tron_N7_P3", "7;3"), ("tron_N8_P2", "8;2"),
+                         ("tron_N21_P4", "21;4"), ("tron_N11_P6", "11;6")):      # the last two: the wide path
         g = np.load(os.path.join(GOLDEN, name + ".npz"))
         P = int(g["P"])
         env = TronGridEnvironment(config)

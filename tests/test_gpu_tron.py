@@ -59,3 +59,19 @@ def test_packed_actions(be):
 
 def test_start_positions_golden(be):
     cases.case_start_positions_golden(be)
+
+
+def test_wide_rollout_vs_oracle(be):
+    # shapes beyond N <= 19, P <= 4 (csrc/tron_wide.cuh): policy + step + fused rollout + statistics vs the oracle
+    cases.case_rollout_vs_oracle(be, N=21, P=4, B=300, K=60, seed=4)
+    cases.case_rollout_vs_oracle(be, N=11, P=6, B=500, K=40, seed=5)
+    cases.case_rollout_vs_oracle(be, N=25, P=8, B=2000, K=50, seed=6, env0=77)
+
+
+def test_wide_adversarial(be):
+    cases.case_wide_adversarial(be)
+
+
+def test_wide_in_place_and_masked_reset(be):
+    cases.case_in_place_and_masked_reset(be, N=21, P=4)
+    cases.case_in_place_and_masked_reset(be, N=11, P=6, B=130)

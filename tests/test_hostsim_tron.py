@@ -51,3 +51,16 @@ def test_packed_actions(be):
 
 def test_start_positions_golden(be):
     cases.case_start_positions_golden(be)
+
+
+def test_wide_rollout_vs_oracle(be):
+    cases.case_rollout_vs_oracle(be, N=21, P=4, B=40, K=40, seed=4)
+    cases.case_rollout_vs_oracle(be, N=11, P=6, B=70, K=30, seed=5)
+
+
+def test_wide_adversarial(be):
+    cases.case_wide_adversarial(be, n=120)
+
+
+def test_wide_in_place_and_masked_reset(be):
+    cases.case_in_place_and_masked_reset(be, N=11, P=6, B=40)
