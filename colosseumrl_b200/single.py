@@ -5,7 +5,8 @@ and the RLlib wrappers (`envs/wrappers/rllib.py:37-55`).
 
 States are *reference-layout* objects (the same tuples of numpy arrays / attribute names the reference's games use),
 so code that peeks into a state (`state[0]` is the Tron board, `state[0].board_contents` the Blokus board, ...) keeps
-working, `next_state` is functional like the reference's, and `serialize_state` is a plain pickle of those objects.
+working, `next_state` is functional like the reference's, and `serialize_state` writes the reference's own wire
+format (wire.py: the stream names the reference's class paths, so an untouched reference client can load it).
 Every call packs the state into the engine's bit-packed layout, runs the same CUDA kernels the batched classes use
 and unpacks the result: there is no CPU implementation of the dynamics here, and no GPU means `CrlError`.
 
@@ -15,13 +16,13 @@ Differences from the reference, all deliberate:
   * a Blokus action string that is not in the mover's valid list is applied as a pass (the reference applies it
     blindly, BlokusEnvironment.py:419-422); `is_valid_action` tells them apart beforehand, as the server does.
 """
-import pickle
 from typing import Dict, List
 
 import numpy as np
 import torch
 
 from . import blokus as _blokus
+from . import wire
 from .blokus import BatchedBlokusEnvironment
 from .tictactoe import BatchedTicTacToe2PlayerEnv, BatchedTicTacToe3PlayerEnv, BatchedTicTacToe4PlayerEnv
 from .tron import BatchedTronGridEnvironment
@@ -64,11 +65,14 @@ class SingleEnvironment:
 
     @staticmethod
     def serialize_state(state) -> bytes:
-        return pickle.dumps(state)
+        """The reference's wire format (`dill.dumps(state)`, BlokusEnvironment.py:305-320): a Blokus state names the
+        reference's own class paths, so an untouched `ClientEnvironment.full_state` rebuilds it (wire.py)."""
+        return wire.dumps(state)
 
     @staticmethod
     def deserialize_state(serialized_state: bytes):
-        return pickle.loads(serialized_state)
+        """Reads the reference's own serialized states as well as ours (wire.py)."""
+        return wire.loads(serialized_state)
 
     @staticmethod
     def _np(t: torch.Tensor) -> np.ndarray:
@@ -158,9 +162,14 @@ class Board:
 class AI:
     """Look-alike of envs/blokus/ai.py:AI: colour, remaining piece names (PIECE_TYPES order), score."""
     def __init__(self, color, pieces=None, score=0):
+        self.player_score = int(score)
         self.player_color = color
         self.current_pieces = list(_blokus.PIECE_NAMES) if pieces is None else list(pieces)
-        self.player_score = int(score)
+
+
+# on the wire the two look-alikes carry the reference's class paths (wire.py)
+wire.register_lookalike("Board", Board)
+wire.register_lookalike("AI", AI)
 
 
 class BlokusEnvironment(SingleEnvironment):

@@ -271,3 +271,23 @@ def test_tron_create():
     assert env.N == 11 and env.num_players == 3 and env.observation_shape["board"] == (11, 11)
     benv = BatchedTronGridEnvironment.create(board_size=9, num_players=2, batch=4)
     assert benv.N == 9 and benv.num_players == 2 and "9x9" in repr(benv)
+
+
+def test_adapter_continues_a_reference_serialized_game():
+    """The bytes an untouched match server pushes (tests/golden/wire_blokus_step20.dill = the reference's own
+    dill.dumps after 20 recorded steps, oracle/make_golden_wire.py) -> deserialize_state -> the engine plays the next
+    recorded steps: valid_actions lists and next_state outputs equal the reference's recording; and our own
+    serialize_state round-trips mid-game."""
+    from colosseumrl_b200.single import BlokusEnvironment
+    g = np.load(os.path.join(GOLDEN, "blokus_games.npz"))
+    env = BlokusEnvironment()
+    state = env.deserialize_state(open(os.path.join(GOLDEN, "wire_blokus_step20.dill"), "rb").read())
+    players = [int(g["mover"][20])]
+    for i in range(20, 32):
+        exp = g["valid_flat"][g["valid_off"][i]:g["valid_off"][i + 1]]
+        assert env.valid_actions(state, players[0]) == ([orc.blokus_action_to_string(int(a)) for a in exp] or [""])
+        state, players, rewards, terminal, winners = env.next_state(state, players, [orc.blokus_action_to_string(int(g["action"][i]))])
+        assert (state[0].board_contents == g["board"][i]).all() and players[0] == g["next_mover"][i]
+        assert [p.player_score for p in state[2]] == g["scores"][i].tolist() and rewards[0] == g["reward"][i]
+        if i == 25:
+            state = env.deserialize_state(env.serialize_state(state))
