@@ -146,7 +146,8 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         Returns (new_state, new_players mask, reward int8 [B] (mover's), terminal uint8 [B], winners mask uint8 [B])."""
         new = self.step_(state, actions, out)
         r = new.result
-        return new, (1 << r[:, 4].to(torch.int32)).to(torch.uint8), r[:, 0].view(torch.int8), r[:, 1] & 1, r[:, 2]
+        # views of the record only (bytes 5 / 6 are the players mask and the terminal flag as plain bytes): no launches
+        return new, r[:, 5], r[:, 0].view(torch.int8), r[:, 6], r[:, 2]
 
     def step_(self, state: BlokusBatchState, actions, out: Optional[BlokusBatchState] = None) -> BlokusBatchState:
         """The bare crl_blokus_step launch (out may be `state` itself: in place).  Outputs are in new.result."""

@@ -468,7 +468,10 @@ blokus_legal_kernel(const uint4 *__restrict__ st, int32_t *__restrict__ counts, 
 
 // ---- next_state: one warp per game.
 // result record, 8 bytes: int8 reward | u8 flags (1 terminal, 2 illegal action, 4 placed) | u8 winners mask |
-//                         u8 ranking bits (bit p = rank of p: winners 0, others 1) | u8 next mover | 3 unused
+//                         u8 ranking bits (bit p = rank of p: winners 0, others 1) | u8 next mover |
+//                         u8 next-players mask (1 << next mover) | u8 terminal (0 / 1) | 1 unused
+//                         (the last two repeat information as plain bytes so that the host layer returns VIEWS of the
+//                         record -- next_state's new_players and terminal -- without any element-wise decoding launch)
 __global__ void __launch_bounds__(32 * BLK_WARPS)
 blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, const int32_t *__restrict__ actions,
                    uint2 *__restrict__ result, crl_u64 *stats, long long B, int flags) {
@@ -556,7 +559,7 @@ blokus_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ outst, cons
             const uint32_t rank = 0xfu & ~(uint32_t)winners;
             result[g] = make_uint2(((uint32_t)reward & 0xffu) | (uint32_t)(terminal | error << 1 | placed << 2) << 8 |
                                        (uint32_t)winners << 16 | rank << 24,
-                                   (uint32_t)nmover);
+                                   (uint32_t)nmover | (1u << nmover) << 8 | (uint32_t)terminal << 16);
             if (stats) {
                 atomicAdd(&sm_stat[ST_STEPS], 1);
                 if (error) atomicAdd(&sm_stat[ST_ERRORS], 1);

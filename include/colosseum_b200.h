@@ -188,7 +188,8 @@ int crl_ttt_pack(void *state, const int8_t *board, const int8_t *winner, const i
  * "{piece};({x}, {y});{orientation}{shift}" (BlokusEnvironment.py:55-106; piece in PIECE_TYPES order, board.py:24-44;
  * orientation in ORIENTATIONS order, board.py:47); -1 = '' (pass).
  * result: 8 bytes per game: int8 reward (mover's) | u8 flags (1 terminal, 2 illegal action, 4 placed) |
- *         u8 winners mask | u8 ranking bits (bit p = rank of p: winners 0, others 1) | u8 next mover | 3 unused.  */
+ *         u8 winners mask | u8 ranking bits (bit p = rank of p: winners 0, others 1) | u8 next mover |
+ *         u8 next-players mask (1 << next mover) | u8 terminal (0 / 1) | 1 unused.  */
 int64_t crl_blokus_state_bytes(int64_t B);
 /* new_state (BlokusEnvironment.py:248-289) */
 int crl_blokus_reset(void *state, const uint8_t *mask_or_null, int64_t B, crl_stream_t stream);

@@ -14,7 +14,8 @@ def unpack_result(res):
     res = np.asarray(res).view(np.uint8).reshape(-1, 8)
     return dict(reward=res[:, 0].view(np.int8).astype(np.int64), terminal=(res[:, 1] & 1).astype(bool),
                 error=(res[:, 1] >> 1 & 1).astype(bool), placed=(res[:, 1] >> 2 & 1).astype(bool),
-                winners=res[:, 2].astype(np.int64), ranking=res[:, 3].astype(np.int64), next_mover=res[:, 4].astype(np.int64))
+                winners=res[:, 2].astype(np.int64), ranking=res[:, 3].astype(np.int64), next_mover=res[:, 4].astype(np.int64),
+                players_mask=res[:, 5].astype(np.int64), terminal_byte=res[:, 6].astype(np.int64))
 
 
 def blk_pack(be, board, inv, scores, rounds, movers, terminal=None, ep_len=None):
@@ -91,6 +92,7 @@ def case_golden_games(be):
     assert (r["winners"] == g["winners"]).all() and (r["next_mover"] == g["next_mover"]).all()
     assert not r["error"].any() and (r["placed"] == (g["action"] >= 0)).all()
     assert (r["ranking"][r["terminal"]] == (0xf & ~r["winners"][r["terminal"]])).all()
+    assert (r["players_mask"] == 1 << g["next_mover"]).all() and (r["terminal_byte"] == g["terminal"]).all()
     # observations
     idx = g["obs_idx"]
     sub = blk_pack(be, g["board"][idx], g["inventory"][idx], g["scores"][idx], g["round"][idx], g["next_mover"][idx])

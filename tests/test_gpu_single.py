@@ -5,6 +5,8 @@ import os
 import numpy as np
 import pytest
 
+from oracle import oracle as orc
+
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
