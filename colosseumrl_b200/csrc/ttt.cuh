@@ -8,11 +8,14 @@
 //   new_state                              :139-170
 //   state_to_observation                   :382-407 (+ the "% 3" relabel quirk of tictactoe_4p_env.py:50)
 //
-// HBM layout: ONE 16-byte vector per environment, uint4 state[B]:
-//   .x = cells of player 0 (bit = C-order flat cell index, <= 27 bits) | mover << 27 | (winner + 1) << 29
-//   .y = cells of player 1 | min(episode steps, 31) << 27
-//   .z = cells of player 2,   .w = cells of player 3
-// A warp loads/stores 512 contiguous bytes per instruction; one thread owns one environment.
+// HBM layout: ONE 16-byte vector per environment, uint4 state[B], MOVER-RELATIVE: word j holds the cells of the
+// player who moves j turns from now,
+//   .x = cells of the mover (bit = C-order flat cell index, <= 27 bits) | mover << 27 | (winner + 1) << 29
+//   .y = cells of player (mover + 1) % n | min(episode steps, 31) << 27
+//   .z = cells of player (mover + 2) % n,   .w = cells of player (mover + 3) % n       (words >= n are zero)
+// so a move is `x |= bit` followed by a rotation of the four words (register renaming): no 4-way select on the mover
+// to find its cells and none to write them back (the seat-indexed layout spent 13 ALU-pipe instructions per step on
+// those).  A warp loads/stores 512 contiguous bytes per instruction; one thread owns one environment.
 //
 // Win test: for every line direction d (4 in 2-D, 13 in 3-D) with flat stride s_d, three in a row exists iff
 //   m & (m >> s_d) & (m >> 2 s_d) & START_d != 0,  START_d = cells where a length-3 segment along d fits.
@@ -35,7 +38,7 @@ struct TTTParams {
 };
 
 struct TTTEnv {
-    uint32_t m[4];
+    uint32_t c[4];       // MOVER-RELATIVE: c[j] = cells of player (mover + j) % n
     int mover, winner1;  // winner1 = winner + 1, 0 = None
     uint32_t ep_len;
 };
@@ -46,27 +49,37 @@ struct TTTOut {
 };
 
 __device__ __forceinline__ void ttt_decode(TTTEnv &s, uint4 v) {
-    s.m[0] = v.x & 0x07ffffffu; s.m[1] = v.y & 0x07ffffffu; s.m[2] = v.z & 0x07ffffffu; s.m[3] = v.w & 0x07ffffffu;
+    s.c[0] = v.x & 0x07ffffffu; s.c[1] = v.y & 0x07ffffffu; s.c[2] = v.z & 0x07ffffffu; s.c[3] = v.w & 0x07ffffffu;
     s.mover = (v.x >> 27) & 3; s.winner1 = (v.x >> 29) & 7;
     s.ep_len = v.y >> 27;
 }
 __device__ __forceinline__ uint4 ttt_encode(const TTTEnv &s) {
-    return make_uint4(s.m[0] | (uint32_t)s.mover << 27 | (uint32_t)s.winner1 << 29,
-                      s.m[1] | min(s.ep_len, 31u) << 27, s.m[2], s.m[3]);
+    return make_uint4(s.c[0] | (uint32_t)s.mover << 27 | (uint32_t)s.winner1 << 29,
+                      s.c[1] | min(s.ep_len, 31u) << 27, s.c[2], s.c[3]);
 }
 __device__ __forceinline__ void ttt_new_state(TTTEnv &s) {
-    s.m[0] = s.m[1] = s.m[2] = s.m[3] = 0; s.mover = 0; s.winner1 = 0; s.ep_len = 0;
+    s.c[0] = s.c[1] = s.c[2] = s.c[3] = 0; s.mover = 0; s.winner1 = 0; s.ep_len = 0;
 }
 template <int NP>
 __device__ __forceinline__ bool ttt_is_terminal(const TTTEnv &s) {
-    return s.winner1 != 0 || ((s.m[0] | s.m[1] | s.m[2] | s.m[3]) == TTTGeo<NP>::CELLMASK);
+    return s.winner1 != 0 || ((s.c[0] | s.c[1] | s.c[2] | s.c[3]) == TTTGeo<NP>::CELLMASK);
+}
+// cells of absolute player p (observation / export side): the word (p - mover) mod NP
+template <int NP>
+__device__ __forceinline__ uint32_t ttt_cells_of(const TTTEnv &s, int p) {
+    int j = p - s.mover;
+    j += j < 0 ? NP : 0;
+    uint32_t r = 0;
+#pragma unroll
+    for (int q = 0; q < NP; q++) r |= (q == j) ? s.c[q] : 0u;
+    return r;
 }
 
 // next_state (tictactoe_2p_env.py:283-315).  action: C-order flat cell index, negative = '' (pass).
 template <int NP>
 __device__ __forceinline__ void ttt_step_env(TTTEnv &s, int action, TTTOut &o) {
     constexpr uint32_t CELLMASK = TTTGeo<NP>::CELLMASK;
-    uint32_t occ = s.m[0] | s.m[1] | s.m[2] | s.m[3];
+    uint32_t occ = s.c[0] | s.c[1] | s.c[2] | s.c[3];
     o.nvalid = __popc(~occ & CELLMASK);
     const bool in_range = (unsigned)action < (unsigned)TTTGeo<NP>::CELLS;
     const uint32_t bit = in_range ? (1u << action) : 0u;
@@ -74,13 +87,9 @@ __device__ __forceinline__ void ttt_step_env(TTTEnv &s, int action, TTTOut &o) {
     const bool placed = cell_free && s.winner1 == 0;                 // :293
     o.error = (action >= 0 && !cell_free) ? 1 : 0;                   // invalid action: silent no-op in the reference
     o.placed = placed;
+    uint32_t mine = s.c[0];                                          // the mover's cells are word 0
     if (placed) {
-        uint32_t mine = 0;
-#pragma unroll
-        for (int p = 0; p < NP; p++) {
-            s.m[p] |= (p == s.mover) ? bit : 0u;                     // :295
-            mine |= (p == s.mover) ? s.m[p] : 0u;
-        }
+        mine |= bit;                                                 // :295
         if (TTTGeo<NP>::win(mine)) s.winner1 = s.mover + 1;          // :297-300
         occ |= bit;
     }
@@ -92,7 +101,11 @@ __device__ __forceinline__ void ttt_step_env(TTTEnv &s, int action, TTTOut &o) {
     }
     if (occ == CELLMASK) o.terminal = 1;                             // :310-311 draw / full board
     o.valid_after = ~occ & CELLMASK;
-    s.mover = (s.mover + 1 == NP) ? 0 : s.mover + 1;                 // :313
+    // the turn passes (:313): every word moves one seat closer to the move, the old mover goes to the back
+#pragma unroll
+    for (int j = 0; j + 1 < NP; j++) s.c[j] = s.c[j + 1];
+    s.c[NP - 1] = mine;
+    s.mover = (s.mover + 1 == NP) ? 0 : s.mover + 1;
     s.ep_len += 1;
 }
 
@@ -128,6 +141,8 @@ __constant__ uint32_t TTT_STAT_LANE[32] = {
 struct TTTStatAcc {
     uint32_t A, W, D, R;
     __device__ __forceinline__ void clear() { A = W = D = R = 0u; }
+    // fused rollout: its rewards are accumulated without the +4 bias per env-step that flush() removes
+    __device__ __forceinline__ void bias_from_steps() { R += 4u * (A & 255u); }
     // one env-step of a live thread
     template <int NP>
     __device__ __forceinline__ void add(const TTTOut &o, int mover, uint32_t ep_len) {
@@ -193,18 +208,29 @@ ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int
     }
 }
 
-// k-th (0-based) set bit of a <= 27-bit mask: branch-free binary search on popcounts
-__device__ __forceinline__ int ttt_kth_bit(uint32_t mask, int k) {
-    int pos = 0;
-#pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        const int c = __popc(mask & ((1u << w) - 1u));
-        const bool up = k >= c;
-        k -= up ? c : 0;
-        pos += up ? w : 0;
-        mask = up ? (mask >> w) : mask;
+// One-hot mask of the k-th (0-based) set bit of a <= 27-bit mask: binary search on popcounts, written so that only
+// TWO instructions per level use the ALU pipe (the binding pipe of the fused rollout kernel,
+// profiles/r02_ttt_rollout_full.md): the search window is a constant times the running one-hot position (IMAD, FMA
+// pipe), the count is a POPC (XU pipe), and the updates are predicated IMADs.  (The first version -- shift the mask
+// down, SEL the three values -- spent 5 ALU instructions per level plus a final 1 << pos.)
+__device__ __forceinline__ uint32_t ttt_kth_bit_onehot(uint32_t mask, uint32_t k) {
+    uint32_t bit = 1u;
+#ifndef CRL_HOSTSIM
+#define TTT_KTH_LEVEL(WIN, MUL)                                                                                          \
+    "mul.lo.u32 t, %0, " WIN ";\n\tand.b32 t, t, %2;\n\tpopc.b32 c, t;\n\tsetp.ge.u32 p, %1, c;\n\t"                      \
+    "@p sub.u32 %1, %1, c;\n\t@p mul.lo.u32 %0, %0, " MUL ";\n\t"
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 c, t;\n\t"
+        TTT_KTH_LEVEL("0xffff", "0x10000") TTT_KTH_LEVEL("0xff", "0x100") TTT_KTH_LEVEL("0xf", "0x10")
+        TTT_KTH_LEVEL("0x3", "0x4") TTT_KTH_LEVEL("0x1", "0x2")
+        "}" : "+r"(bit), "+r"(k) : "r"(mask));
+#undef TTT_KTH_LEVEL
+#else
+    for (uint32_t w = 16; w >= 1; w >>= 1) {
+        const uint32_t c = (uint32_t)__popc(mask & (((1u << w) - 1u) * bit));
+        if (k >= c) { k -= c; bit <<= w; }
     }
-    return pos;
+#endif
+    return bit;
 }
 
 // Exact r % n for n <= 27 without the generic 32-bit division (~20 instructions): lane l holds floor(2^32 / l), a
@@ -219,17 +245,22 @@ __device__ __forceinline__ uint32_t ttt_rcp_lane() { return TTT_RCP_G[threadIdx.
 __device__ __forceinline__ uint32_t ttt_mod_small(uint32_t r, uint32_t n, uint32_t rcp_lane) {
     const uint32_t m = __shfl_sync(0xffffffffu, rcp_lane, (int)n);
     uint32_t rem = r - __umulhi(r, m) * n;
+#ifndef CRL_HOSTSIM
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %0, %1;\n\t@p sub.u32 %0, %0, %1;\n\t}" : "+r"(rem) : "r"(n));   // (a predicated IMAD, not a SEL)
+    return rem;
+#else
     return rem >= n ? rem - n : rem;
+#endif
 }
 
 // uniform random policy: the (r0 % n_empty)-th empty cell in C order, pass (-1) if the board is full
 // (warp-collective because of ttt_mod_small)
 template <int NP>
 __device__ __forceinline__ int ttt_random_action(const TTTEnv &s, uint32_t r0, uint32_t rcp_lane) {
-    uint32_t empty = ~(s.m[0] | s.m[1] | s.m[2] | s.m[3]) & TTTGeo<NP>::CELLMASK;
+    uint32_t empty = ~(s.c[0] | s.c[1] | s.c[2] | s.c[3]) & TTTGeo<NP>::CELLMASK;
     const int n = __popc(empty);
     const uint32_t k = ttt_mod_small(r0, (uint32_t)max(n, 1), rcp_lane);
-    return n ? ttt_kth_bit(empty, (int)k) : -1;
+    return n ? 31 - __clz((int)ttt_kth_bit_onehot(empty, k)) : -1;
 }
 
 template <int NP>
@@ -246,30 +277,59 @@ __global__ void ttt_policy_random_kernel(const uint4 *__restrict__ st, int8_t *_
     if (valid) actions[e] = (int8_t)a;
 }
 
-// One fused random-policy step of a NON-terminal environment (the rollout resets terminal ones first): a non-terminal
-// board has an empty cell and no winner, so the chosen cell is always free and always placed -- next_state
-// (tictactoe_2p_env.py:283-315) without its validity branches, sharing the empty mask with the policy.
+// ---- fused random-policy step on the RAW state words (mover-relative layout, fields in the top five bits of x / y).
+// A non-terminal board has an empty cell and no winner, so the chosen cell is always free and always placed:
+// next_state (tictactoe_2p_env.py:283-315) without its validity branches, sharing the empty mask with the policy.
+// Written against the ALU pipe: the cells are never masked out of their words (the win test only shifts LEFT and ends
+// with an AND against masks inside the cell bits, so the field bits above them cannot reach it), the move is
+// x |= bit, the turn passes by renaming the four words, and the field updates are adds of disjoint bit ranges (IMAD).
+struct TTTFusedOut {
+    uint32_t win, terminal;      // 0 / 1
+    uint32_t mover, n;           // the player who moved, number of empty cells before the move
+    uint32_t ep_top;             // new (saturated) episode length << 27
+};
+
 template <int NP>
-__device__ __forceinline__ void ttt_policy_step(TTTEnv &s, uint32_t r0, uint32_t rcp_lane, TTTOut &o) {
-    constexpr uint32_t CELLMASK = TTTGeo<NP>::CELLMASK;
-    const uint32_t occ = s.m[0] | s.m[1] | s.m[2] | s.m[3], empty = ~occ & CELLMASK;
-    const int n = __popc(empty);                                     // >= 1
-    const uint32_t bit = 1u << ttt_kth_bit(empty, (int)ttt_mod_small(r0, (uint32_t)max(n, 1), rcp_lane));
-    // the mover's cells: a 4:1 multiplexer on the two mover bits (3 selects), then one predicated write-back per seat
-    const bool b0 = (s.mover & 1) != 0, b1 = (s.mover & 2) != 0;
-    const uint32_t lo = b0 ? s.m[1] : s.m[0], hi = b0 ? s.m[3 % NP] : s.m[2 % NP];
-    const uint32_t mine = ((NP > 2 && b1) ? hi : lo) | bit;
-#pragma unroll
-    for (int p = 0; p < NP; p++) s.m[p] = (p == s.mover) ? mine : s.m[p];
+__device__ __forceinline__ void ttt_policy_step_raw(uint4 &v, uint32_t empty, uint32_t r0, uint32_t rcp_lane, TTTFusedOut &o) {
+    constexpr uint32_t CM = 0x07ffffffu;                 // the cell bits of a word (the fields sit above, whatever NP)
+    const uint32_t n = (uint32_t)__popc(empty);          // >= 1
+    const uint32_t bit = ttt_kth_bit_onehot(empty, ttt_mod_small(r0, n, rcp_lane));
+    const uint32_t mine = v.x | bit;                     // raw: mover in bits 27..28, winner bits zero
     const bool win = TTTGeo<NP>::win(mine) != 0u;
-    s.winner1 = win ? s.mover + 1 : 0;
-    o.nvalid = n; o.error = 0; o.placed = 1;
-    o.reward = win ? 1 : 0;
-    o.winners = win ? 1 << s.mover : 0;
-    o.terminal = (win || (occ | bit) == CELLMASK) ? 1 : 0;
-    o.valid_after = ~(occ | bit) & CELLMASK;
-    s.mover = NP == 4 ? ((s.mover + 1) & 3) : ((s.mover + 1 == NP) ? 0 : s.mover + 1);
-    s.ep_len += 1;
+    const uint32_t mover = v.x >> 27;
+    const uint32_t t1 = mover + 1u;
+    uint32_t f0 = (NP == 4 ? (t1 & 3u) : (t1 == (uint32_t)NP ? 0u : t1)) << 27;           // next mover
+    uint32_t top1 = v.y & ~CM;                           // episode length, saturating at 31
+#ifndef CRL_HOSTSIM
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p mad.lo.u32 %0, %2, 0x20000000, %0;\n\t}" : "+r"(f0) : "r"((uint32_t)win), "r"(t1));
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %0, 0xf8000000;\n\t@p add.u32 %0, %0, 0x08000000;\n\t}" : "+r"(top1));
+#else
+    if (win) f0 += t1 << 29;
+    if (top1 < 0xf8000000u) top1 += 0x08000000u;
+#endif
+    o.win = win ? 1u : 0u;
+    o.terminal = (win || empty == bit) ? 1u : 0u;
+    o.mover = mover; o.n = n; o.ep_top = top1;
+    const uint32_t back = mine & CM;                     // the mover's cells go to the back of the queue
+    if (NP == 4) v = make_uint4((v.y & CM) | f0, v.z + top1, v.w, back);
+    else if (NP == 3) v = make_uint4((v.y & CM) | f0, v.z + top1, back, 0u);
+    else v = make_uint4((v.y & CM) | f0, back + top1, 0u, 0u);
+}
+
+// result record of a fused step (reward = 1 for a winning move, the winner is the mover)
+template <int NP>
+__device__ __forceinline__ uint32_t ttt_fused_result(const TTTFusedOut &o) {
+    const uint32_t wm = o.win << o.mover;                                   // winners mask
+    return o.win | (o.terminal | 4u) << 8 | wm << 16 | ((((1u << NP) - 1u) ^ wm) << 24);
+}
+
+// episode statistics of a fused step into the packed counters of TTTStatAcc; the reward bias the flush removes is
+// added once per flush (TTTStatAcc::bias_from_steps)
+__device__ __forceinline__ void ttt_fused_stats(TTTStatAcc &acc, const TTTFusedOut &o) {
+    acc.A += 1u + (o.terminal ? (o.win ? 0x100u : 0x10100u) : 0u);           // steps | episodes << 8 | episodes without a winner << 16
+    acc.W += ((o.win << o.mover) * 0x00204081u) & 0x01010101u;              // bit q -> byte q
+    acc.D += o.n + (o.terminal ? (o.ep_top >> 27) << 12 : 0u);
+    acc.R += o.win ? o.mover + 1u : 0u;
 }
 
 // K fused random-policy steps with auto-reset; grid-stride like the step kernel (a thread owns <= TTT_ACC_MAX
@@ -278,6 +338,7 @@ template <int NP>
 __global__ void __launch_bounds__(256, 8)
 ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl_u64 *stats, long long B,
                    const PhiloxKeys keys, crl_u64 first_env, uint32_t step0, int K) {
+    constexpr uint32_t CM = TTTGeo<NP>::CELLMASK;
     __shared__ int sm_stat[CRL_NSTAT];
     if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
     const uint32_t lane_const = TTT_STAT_LANE[threadIdx.x & 31], rcp_lane = ttt_rcp_lane();
@@ -290,27 +351,33 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
     for (long long e0 = first; e0 < B; e0 += stride) {   // block-uniform trip count: the flushes are warp-collective
         const long long e = e0 + threadIdx.x;
         const bool valid = e < B;
-        TTTEnv s;
-        TTTOut o;
-        ttt_zero_out(o);
-        ttt_new_state(s);
-        if (valid) ttt_decode(s, ld_stream(state + e));
-        for (int k = 0; k < K; k++) {                    // (lanes past the end of the batch step a dummy board)
-            if (ttt_is_terminal<NP>(s)) ttt_new_state(s);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);            // (lanes past the end of the batch step a dummy board)
+        if (valid) v = ld_stream(state + e);
+        TTTFusedOut o;
+        o.win = o.terminal = o.mover = o.n = o.ep_top = 0u;
+        for (int k = 0; k < K; k++) {
+            uint32_t empty = ~(v.x | v.y | v.z | v.w) & CM;
+            if (v.x >= 0x20000000u || empty == 0u) {     // terminal (a winner, or a full board): new_state
+                v = make_uint4(0u, 0u, 0u, 0u);
+                empty = CM;
+            }
             const crl_u64 ge = first_env + (crl_u64)e;
             const uint32_t r0 = philox4x32_10_x((uint32_t)ge, (uint32_t)(ge >> 32), step0 + (uint32_t)k, CRL_TAG_TTT, keys);
-            const int mover = s.mover;
-            ttt_policy_step<NP>(s, r0, rcp_lane, o);
-            if (stats && valid) acc.add<NP>(o, mover, s.ep_len);
-            if (stats && ++pending == TTT_ACC_MAX) { acc.flush<NP>(sm_stat, lane_const); pending = 0; }
+            ttt_policy_step_raw<NP>(v, empty, r0, rcp_lane, o);
+            if (stats && valid) ttt_fused_stats(acc, o);
+            if (stats && ++pending == TTT_ACC_MAX) {
+                acc.bias_from_steps();
+                acc.flush<NP>(sm_stat, lane_const);
+                pending = 0;
+            }
         }
         if (valid) {
-            st_stream(state + e, ttt_encode(s));
-            if (result) result[e] = ttt_pack_result<NP>(o);
+            st_stream(state + e, v);
+            if (result) result[e] = ttt_fused_result<NP>(o);
         }
     }
     if (stats) {
-        if (pending) acc.flush<NP>(sm_stat, lane_const);
+        if (pending) { acc.bias_from_steps(); acc.flush<NP>(sm_stat, lane_const); }
         __syncthreads();
         stats_flush_row(sm_stat, stats);
     }
@@ -359,12 +426,14 @@ ttt_observe_kernel(const uint4 *__restrict__ st, long long B, int player, int8_t
     const int viewer = player == -2 ? s.mover : player;
     uint32_t b0 = 0u, b1 = 0u;
 #pragma unroll
-    for (int p = 0; p < NP; p++) {
+    for (int j = 0; j < NP; j++) {                           // word j = player (mover + j) % NP
+        int p = s.mover + j;
+        p -= p >= NP ? NP : 0;
         const int code = viewer < 0 ? p : ((p - viewer) % MOD + MOD) % MOD;
-        b0 |= (code & 1) ? s.m[p] : 0u;
-        b1 |= (code & 2) ? s.m[p] : 0u;
+        b0 |= (code & 1) ? s.c[j] : 0u;
+        b1 |= (code & 2) ? s.c[j] : 0u;
     }
-    const uint32_t emp = ~(s.m[0] | s.m[1] | s.m[2] | s.m[3]);
+    const uint32_t emp = ~(s.c[0] | s.c[1] | s.c[2] | s.c[3]);
     uint8_t *mine = stage[wid] + lane * CELLS;
 #pragma unroll
     for (int j = 0; j < GROUPS; j++) {
@@ -393,12 +462,14 @@ __global__ void ttt_pack_kernel(uint4 *__restrict__ st, long long B, TTTParams p
     if (e >= B) return;
     TTTEnv s;
     ttt_new_state(s);
-    for (int c = 0; c < prm.cells; c++) {
-        int v = board[e * prm.cells + c];
-#pragma unroll
-        for (int p = 0; p < 4; p++) s.m[p] |= (v == p) ? (1u << c) : 0u;
-    }
     s.winner1 = winner[e] + 1;
     s.mover = mover[e];
+    for (int c = 0; c < prm.cells; c++) {
+        const int v = board[e * prm.cells + c];
+        int j = v - s.mover;                                 // player v sits in word (v - mover) mod n
+        j += j < 0 ? prm.n : 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) s.c[q] |= (v >= 0 && q == j) ? (1u << c) : 0u;
+    }
     st[e] = ttt_encode(s);
 }

@@ -93,7 +93,7 @@ def test_tron_api_wide_shapes():
             env.host_stepper(state, compact=2)
 
 
-def test_ttt_api():"""
+def test_ttt_api():
     from colosseumrl_b200.tictactoe import BatchedTicTacToe4PlayerEnv, BatchedTicTacToe2PlayerEnv
     B, seed = 300, 2
     env = BatchedTicTacToe4PlayerEnv(batch=B, seed=seed, auto_reset=True)
