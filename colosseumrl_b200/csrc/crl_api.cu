@@ -624,11 +624,18 @@ int crl_ttt_rollout(void *state, uint8_t *result, int64_t *stats, uint64_t seed,
     if (rc) return rc;
     if (!state || B < 0 || K < 0) return fail(CRL_ERR_ARG, "crl_ttt_rollout: bad argument%s");
     if (B == 0 || K == 0) return CRL_OK;
+    if (B >= (int64_t)1 << 31) return fail(CRL_ERR_UNSUPPORTED, "crl_ttt_rollout: batch too large for one launch%s");
     const PhiloxKeys keys = philox_expand_keys((crl_u64)seed);
-#define TTT_ROLL(NP) CRL_LAUNCH_PDL(ttt_rollout_kernel<NP>, ttt_blocks(B), 256, (cudaStream_t)stream, (uint4 *)state, \
-                               (uint32_t *)result, (crl_u64 *)stats, (long long)B, keys, (crl_u64)first_env, step0, K)
+    // resident CTAs per SM the register allocation aims at (CRL_TTT_MINB=8: 32 registers, the round-1 setting)
+    static const int minb = getenv("CRL_TTT_MINB") ? atoi(getenv("CRL_TTT_MINB")) : TTT_ROLLOUT_MINB;
+#define TTT_ROLL3(NP, ST, MB) CRL_LAUNCH_PDL((ttt_rollout_kernel<NP, ST, MB>), ttt_blocks(B), 256, (cudaStream_t)stream, (uint4 *)state, \
+                                        (uint32_t *)result, (crl_u64 *)stats, (int)B, keys, (crl_u64)first_env, step0, K)
+#define TTT_ROLL2(NP, ST) do { if (minb == 8) TTT_ROLL3(NP, ST, 8); else TTT_ROLL3(NP, ST, 6); } while (0)
+#define TTT_ROLL(NP) do { if (stats) TTT_ROLL2(NP, true); else TTT_ROLL2(NP, false); } while (0)
     if (n == 2) TTT_ROLL(2); else if (n == 3) TTT_ROLL(3); else TTT_ROLL(4);
 #undef TTT_ROLL
+#undef TTT_ROLL2
+#undef TTT_ROLL3
     return check_launch("ttt_rollout_kernel");
 }
 

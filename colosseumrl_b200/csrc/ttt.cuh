@@ -129,6 +129,7 @@ __device__ __forceinline__ uint32_t ttt_pack_result(const TTTOut &o) {
 //   R: (mover + 1) * reward, biased by +4 per env-step (<= 8 * 128)
 //   lane constants: word (0..3) | shift << 4 | bits << 10 | slot << 16 | kind << 24 (1: episodes - x, 2: x - 4 * steps)
 #define TTT_ACC_MAX 4
+#define TTT_ROLLOUT_MINB 8     // default register budget of the fused rollout kernel (see its template parameter)
 #define TTT_SL(word, shift, bits, slot, kind) ((word) | (shift) << 4 | (bits) << 10 | (slot) << 16 | (kind) << 24)
 __constant__ uint32_t TTT_STAT_LANE[32] = {
     TTT_SL(0, 0, 8, ST_STEPS, 0), TTT_SL(0, 8, 8, ST_EPISODES, 0), TTT_SL(0, 16, 8, ST_NOWIN, 0), TTT_SL(0, 24, 8, ST_ERRORS, 0),
@@ -333,42 +334,46 @@ __device__ __forceinline__ void ttt_fused_stats(TTTStatAcc &acc, const TTTFusedO
 }
 
 // K fused random-policy steps with auto-reset; grid-stride like the step kernel (a thread owns <= TTT_ACC_MAX
-// environments and keeps one of them in registers for the K steps).
-template <int NP>
-__global__ void __launch_bounds__(256, 8)
-ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl_u64 *stats, long long B,
+// environments and keeps one of them in registers for the K steps).  STATS is a template parameter (no per-iteration
+// pointer tests), the batch index is 32-bit (the launcher refuses B >= 2^31), MINB = resident CTAs per SM the register
+// allocation aims at (8: 32 registers; 6: 40 registers, the Philox keys and pointers stay in registers).
+template <int NP, bool STATS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl_u64 *stats, int B,
                    const PhiloxKeys keys, crl_u64 first_env, uint32_t step0, int K) {
     constexpr uint32_t CM = TTTGeo<NP>::CELLMASK;
     __shared__ int sm_stat[CRL_NSTAT];
-    if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
+    if (STATS) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
     const uint32_t lane_const = TTT_STAT_LANE[threadIdx.x & 31], rcp_lane = ttt_rcp_lane();
     TTTStatAcc acc;
     acc.clear();
     int pending = 0;                                     // env-steps accumulated since the last flush (block-uniform)
-    const long long stride = (long long)gridDim.x * blockDim.x, first = (long long)blockIdx.x * blockDim.x;
+    const int stride = (int)(gridDim.x * blockDim.x), first = (int)(blockIdx.x * blockDim.x);
     pdl_wait();
     pdl_launch_dependents();
-    for (long long e0 = first; e0 < B; e0 += stride) {   // block-uniform trip count: the flushes are warp-collective
-        const long long e = e0 + threadIdx.x;
+    for (int e0 = first; e0 < B; e0 += stride) {         // block-uniform trip count: the flushes are warp-collective
+        const int e = e0 + (int)threadIdx.x;
         const bool valid = e < B;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);            // (lanes past the end of the batch step a dummy board)
         if (valid) v = ld_stream(state + e);
         TTTFusedOut o;
         o.win = o.terminal = o.mover = o.n = o.ep_top = 0u;
+        const crl_u64 ge = first_env + (crl_u64)(uint32_t)e;
         for (int k = 0; k < K; k++) {
             uint32_t empty = ~(v.x | v.y | v.z | v.w) & CM;
             if (v.x >= 0x20000000u || empty == 0u) {     // terminal (a winner, or a full board): new_state
                 v = make_uint4(0u, 0u, 0u, 0u);
                 empty = CM;
             }
-            const crl_u64 ge = first_env + (crl_u64)e;
             const uint32_t r0 = philox4x32_10_x((uint32_t)ge, (uint32_t)(ge >> 32), step0 + (uint32_t)k, CRL_TAG_TTT, keys);
             ttt_policy_step_raw<NP>(v, empty, r0, rcp_lane, o);
-            if (stats && valid) ttt_fused_stats(acc, o);
-            if (stats && ++pending == TTT_ACC_MAX) {
-                acc.bias_from_steps();
-                acc.flush<NP>(sm_stat, lane_const);
-                pending = 0;
+            if (STATS) {
+                if (valid) ttt_fused_stats(acc, o);
+                if (++pending == TTT_ACC_MAX) {
+                    acc.bias_from_steps();
+                    acc.flush<NP>(sm_stat, lane_const);
+                    pending = 0;
+                }
             }
         }
         if (valid) {
@@ -376,7 +381,7 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
             if (result) result[e] = ttt_fused_result<NP>(o);
         }
     }
-    if (stats) {
+    if (STATS) {
         if (pending) { acc.bias_from_steps(); acc.flush<NP>(sm_stat, lane_const); }
         __syncthreads();
         stats_flush_row(sm_stat, stats);

@@ -18,8 +18,12 @@ def test_registry_and_surface():
     for name in ("new_state", "next_state", "valid_actions", "is_valid_action", "is_terminal", "compute_ranking",
                  "state_to_observation", "serialize_state", "deserialize_state"):
         assert hasattr(env, name)
+    wide = get_environment("tron")("25;4", batch=8)       # beyond N <= 19: the wide layout (csrc/tron_wide.cuh)
+    assert wide.wide and wide.observation_shape["board"] == (25, 25)
     with pytest.raises(Exception):
-        get_environment("tron")("25;4", batch=8)          # unsupported board size fails loudly
+        get_environment("tron")("65;4", batch=8)          # unsupported board size fails loudly
+    with pytest.raises(Exception):
+        get_environment("tron")("19;9", batch=8)
 
 
 def test_tron_api_episode():
