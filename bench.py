@@ -298,7 +298,10 @@ class TronWL:
         self.h_actions = [torch.from_numpy(BatchedTronGridEnvironment.pack_actions(
             np.random.RandomState(rank + i).randint(-1, 2, size=(B, 4)).astype(np.int8))).pin_memory() for i in range(2)]
         self.h2d, self.d2h = B * 1, B * 2
-        self.stepper_kwargs = {"compact": 2, "packed_actions": True}
+        self.stepper_kwargs = {"compact": 2, "packed_actions": True, "zero_copy": True}
+        self.e2e_note = ("host_stepper(compact=2, packed_actions=True, zero_copy=True): one graph launch per step = ONE kernel "
+                         "node; the step kernel reads the step's packed actions from pinned host memory (64 KB over PCIe, H2D) "
+                         "and writes its 2-byte records to pinned host memory (128 KB, D2H); the host reads a record of every step")
         self.steppers = None
 
     def prepare(self, k0, n):
@@ -728,7 +731,9 @@ def measure_b200(name, args, cx, with_cpu):
                        "parallelism": "env-sharded x%d, no data-path collective, 1 stats all-reduce inside the timed region" % world},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": work.h2d,
-                    "d2h_bytes_per_step": work.d2h, "steps": Ke},
+                    "d2h_bytes_per_step": work.d2h, "steps": Ke,
+                    "transport": getattr(work, "e2e_note", "one graph launch per step = memcpy H2D of the pinned actions + "
+                                         "step kernel + memcpy D2H of the result record into pinned memory")},
             "gpu_launches": n_timed * wl["launches"] * world + world,
             "clocks": clk,
             "wall_s_timed_region": wall,

@@ -38,16 +38,53 @@ class HostStepper:
     An actor that serves two (or more) environment batches can pipeline them: `a.launch(); b.wait(); ...`; give each
     stepper its own `stream` and the copy engines of one batch overlap the step kernel of another.
 
-    Zero-copy access to pinned memory from the kernel was measured ~4x slower than explicit copies (PCIe posted
-    8-byte writes), so the copies stay explicit and the three operations are fused into one graph launch instead.
+    Two transports:
+      * copy engines (default): the graph is  memcpy H2D -> step kernel -> memcpy D2H.  Right for wide records: with
+        the full 8-byte Tron record zero-copy was measured ~4x slower (posted PCIe writes of scattered 8-byte stores).
+      * zero copy (`zero_copy_step`): the step kernel itself reads the actions from and writes the records to the
+        PINNED HOST buffers (a cudaHostAlloc'ed buffer has the same address on the device under UVA), so the graph is
+        ONE kernel node.  With Tron's packed actions (1 B / env, one coalesced 64-byte read per CTA) and 2-byte records
+        (one 128-byte segment per CTA) the PCIe traffic is the same 64 KB up + 128 KB down per step, but the two
+        memcpy nodes -- ~3 us each in stream order, the cost that bounded this leg -- are gone: 8.3 -> 5.7 us per step,
+        7.9 -> 11.6 G env-steps/s (tools/e2e_probe.py; the floor with device-resident buffers is 4.7 us).
     """
 
-    def __init__(self, env, state, action_shape, action_dtype, stream=None, step=None):
+    def __init__(self, env, state, action_shape, action_dtype, stream=None, step=None, zero_copy_step=None,
+                 result_shape=None):
         """step(dev_actions) -> device tensor holding the step's result record; default: env.step_ in place on
-        `state`, the full record.  (Tron passes a compact-record step: half the bytes to read back.)"""
+        `state`, the full record.  (Tron passes a compact-record step: half the bytes to read back.)
+        zero_copy_step(host_actions, host_result): launches the step with the pinned buffers as its action / result
+        arguments (result_shape = shape of the uint8 record buffer)."""
         self.env, self.state, self.stream = env, state, stream
         with torch.cuda.device(env.device):
-            self._build(env, state, action_shape, action_dtype, stream, step)
+            if zero_copy_step is not None:
+                self._build_zero_copy(env, action_shape, action_dtype, result_shape, stream, zero_copy_step)
+            else:
+                self._build(env, state, action_shape, action_dtype, stream, step)
+
+    def _build_zero_copy(self, env, action_shape, action_dtype, result_shape, stream, zstep):
+        self.actions = torch.zeros(action_shape, dtype=action_dtype).pin_memory()
+        self.result = torch.zeros(result_shape, dtype=torch.uint8).pin_memory()
+        self.result_np, self.actions_np = self.result.numpy(), self.actions.numpy()
+        self._step = zstep
+        s = stream if stream is not None else torch.cuda.current_stream(env.device)
+        with torch.cuda.stream(s):
+            zstep(self.actions, self.result)                    # warms the launch path (applies one step)
+        torch.cuda.synchronize(env.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            zstep(self.actions, self.result)
+        self._finish(env, s)
+
+    def _finish(self, env, s):
+        # replay / completion through the CUDA runtime directly: three ctypes calls per step instead of torch's
+        # stream context + event objects (the host loop is CPU-bound)
+        from . import _cudart
+        self._rt = _cudart.rt()
+        self._exec = self.graph.raw_cuda_graph_exec()
+        self._done = _cudart.new_event()
+        self._stream_handle = s.cuda_stream
+        _cudart.check(self._rt.cudaGraphUpload(self._exec, self._stream_handle), "cudaGraphUpload")
 
     def _build(self, env, state, action_shape, action_dtype, stream, step):
         self.actions = torch.zeros(action_shape, dtype=action_dtype).pin_memory()
@@ -68,15 +105,7 @@ class HostStepper:
             self._dev_actions.copy_(self.actions, non_blocking=True)
             self.result.copy_(step(self._dev_actions), non_blocking=True)
 
-        # replay / completion through the CUDA runtime directly: three ctypes calls per step instead of torch's
-        # stream context + event objects (the host loop is CPU-bound)
-        from . import _cudart
-        self._rt = _cudart.rt()
-        self._exec = self.graph.raw_cuda_graph_exec()
-        self._done = _cudart.new_event()
-        s = stream if stream is not None else torch.cuda.current_stream(env.device)
-        self._stream_handle = s.cuda_stream
-        _cudart.check(self._rt.cudaGraphUpload(self._exec, self._stream_handle), "cudaGraphUpload")
+        self._finish(env, stream if stream is not None else torch.cuda.current_stream(env.device))
 
     def launch(self):
         """Enqueue H2D + step + D2H (one graph launch) on the stepper's stream; returns immediately."""

@@ -177,23 +177,36 @@ class BatchedTronGridEnvironment(BatchedBaseEnvironment):
                                     new.result.data_ptr(), self.flags))
         return new
 
-    def host_stepper(self, state: TronBatchState, stream=None, compact=False, packed_actions: bool = False):
+    def host_stepper(self, state: TronBatchState, stream=None, compact=False, packed_actions: bool = False,
+                     zero_copy: bool = False):
         """Graph-fused H2D actions -> step -> D2H result for host-side policies (see base.HostStepper).
         compact=True: the step writes the 4-byte record (CRL_FLAG_COMPACT_RESULT: terminal | alive | winners | ranking),
         which halves the PCIe read-back; compact=2: the 2-byte record (CRL_FLAG_COMPACT2_RESULT: alive | terminal << 4,
         ranking), a quarter -- the read-back is the slowest leg of a host-side actor's step.  `decode_compact`
         rebuilds the reference's return values from either on the host.
         packed_actions=True: the pinned action buffer is uint8 [B], 2 bits per player (`pack_actions`), a quarter of
-        the PCIe upload.  NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
+        the PCIe upload.  zero_copy=True (with compact=2 and packed_actions): the step kernel reads the pinned action
+        buffer and writes the pinned record buffer directly over PCIe -- one kernel node per step instead of memcpy +
+        kernel + memcpy (base.HostStepper).  NOTE: the warm-up inside applies one step of all-forward actions to `state`."""
         from .base import HostStepper
         if self.wide and (compact or packed_actions):
             raise ValueError("compact records / packed actions exist for N <= 19, P <= 4 only")
         if not compact and not packed_actions:
             return HostStepper(self, state, (self.batch, self.action_stride), torch.int8, stream=stream)
         width = 2 if compact == 2 else (4 if compact else 8)
-        rec = torch.empty((self.batch, width), dtype=torch.uint8, device=self.device)
         flags = self.flags | {8: 0, 4: _lib.FLAG_COMPACT_RESULT, 2: _lib.FLAG_COMPACT2_RESULT}[width] | \
             (_lib.FLAG_PACKED_ACTIONS if packed_actions else 0)
+        if zero_copy:
+            if not (compact == 2 and packed_actions):
+                raise ValueError("zero_copy needs compact=2 and packed_actions=True (narrow, coalesced PCIe accesses)")
+
+            def zstep(host_actions, host_result):
+                self._check(self._step_call(state.packed.data_ptr(), state.packed.data_ptr(), host_actions.data_ptr(),
+                                            host_result.data_ptr(), flags))
+                state.result = None
+            return HostStepper(self, state, (self.batch,), torch.uint8, stream=stream, zero_copy_step=zstep,
+                               result_shape=(self.batch, 2))
+        rec = torch.empty((self.batch, width), dtype=torch.uint8, device=self.device)
 
         def step(dev_actions):
             self._check(self._step_call(state.packed.data_ptr(), state.packed.data_ptr(), dev_actions.data_ptr(),

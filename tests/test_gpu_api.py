@@ -191,16 +191,19 @@ def test_host_stepper_matches_next_state():
     assert (sc.packed == sr.packed).all()
 
 
-@pytest.mark.parametrize("compact", [True, 2])
+@pytest.mark.parametrize("compact", [True, 2, "zero_copy"])
 def test_compact_host_stepper(compact):
-    """host_stepper(compact=True / 2): 4- / 2-byte records whose decode equals next_state's return values."""
+    """host_stepper(compact=True / 2): 4- / 2-byte records whose decode equals next_state's return values; and the
+    zero-copy transport (the kernel reads / writes the pinned host buffers itself): same records, same states."""
     from colosseumrl_b200.tron import BatchedTronGridEnvironment
     B = 513
+    zero_copy = compact == "zero_copy"
+    compact = 2 if zero_copy else compact
     a_env = BatchedTronGridEnvironment("", batch=B, seed=4, auto_reset=True)
     b_env = BatchedTronGridEnvironment("", batch=B, seed=4, auto_reset=True)
     sa, _ = a_env.new_state()
     sb, _ = b_env.new_state()
-    stepper = b_env.host_stepper(sb, compact=compact, packed_actions=True)   # warm-up applies one all-forward step
+    stepper = b_env.host_stepper(sb, compact=compact, packed_actions=True, zero_copy=zero_copy)   # warm-up applies one all-forward step
     sa, *_ = a_env.next_state(sa, None, torch.zeros((B, 4), dtype=torch.int8))
     rng = np.random.RandomState(1)
     terminals = 0

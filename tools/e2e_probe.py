@@ -49,3 +49,77 @@ def copies_only(e, s, st):
 
 
 run("copies only (256 KB each way)", copies_only)
+
+
+class ZeroCopyStepper:
+    """Experiment: the step kernel reads the packed actions from and writes the 2-byte records to PINNED HOST memory
+    directly (UVA: a cudaHostAlloc'ed buffer has the same address on the device), so the graph is ONE kernel node -- no
+    copy-engine transfers, no memcpy nodes."""
+
+    def __init__(self, env, state, stream, graph=True, device_buffers=False):
+        from colosseumrl_b200 import _cudart, _lib
+        self.env, self.state = env, state
+        if device_buffers:
+            self.actions = torch.zeros((B,), dtype=torch.uint8, device=env.device)
+            self.result = torch.zeros((B, 2), dtype=torch.uint8, device=env.device)
+        else:
+            self.actions = torch.zeros((B,), dtype=torch.uint8).pin_memory()
+            self.result = torch.zeros((B, 2), dtype=torch.uint8).pin_memory()
+        self.flags = env.flags | _lib.FLAG_COMPACT2_RESULT | _lib.FLAG_PACKED_ACTIONS
+        self._rt = _cudart.rt()
+        self._done = _cudart.new_event()
+        self._stream_handle = stream.cuda_stream
+        self.stream = stream
+        self.graph = None
+        with torch.cuda.stream(stream):
+            self._call()
+        torch.cuda.synchronize()
+        if graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=stream):
+                self._call()
+            self._exec = self.graph.raw_cuda_graph_exec()
+            _cudart.check(self._rt.cudaGraphUpload(self._exec, self._stream_handle), "upload")
+        self.result_np = self.result.numpy() if not device_buffers else None
+
+    def _call(self):
+        e, p = self.env, self.state.packed.data_ptr()
+        e._check(e._step_call(p, p, self.actions.data_ptr(), self.result.data_ptr(), self.flags))
+
+    def launch(self):
+        if self.graph is not None:
+            rc = self._rt.cudaGraphLaunch(self._exec, self._stream_handle)
+        else:
+            with torch.cuda.stream(self.stream):
+                self._call()
+            rc = 0
+        rc = rc or self._rt.cudaEventRecord(self._done, self._stream_handle)
+        assert rc == 0, rc
+
+    def wait(self):
+        assert self._rt.cudaEventSynchronize(self._done) == 0
+        return self.result_np if self.result_np is not None else np.zeros((1, 1), np.uint8)
+
+    def __call__(self):
+        self.launch()
+        return self.wait()
+
+
+run("zero-copy, 1-node graph", lambda e, s, st: ZeroCopyStepper(e, s, st))
+run("device buffers, 1-node graph (floor)", lambda e, s, st: ZeroCopyStepper(e, s, st, device_buffers=True))
+run("zero-copy, direct launch", lambda e, s, st: ZeroCopyStepper(e, s, st, graph=False))
+# parity of the zero-copy path: same states as the copy path after the same actions
+a = ZeroCopyStepper(envs[0], states[0], streams[0])
+b = envs[1].host_stepper(states[1], stream=streams[1], compact=2, packed_actions=True)
+states[1].packed.copy_(states[0].packed)
+torch.cuda.synchronize()
+rng = np.random.RandomState(0)
+for t in range(20):
+    acts = rng.randint(0, 256, size=B).astype(np.uint8)
+    a.actions.numpy()[:] = acts
+    b.actions_np[:] = acts
+    ra, rb = a().copy(), b().copy()
+    assert (ra == rb).all(), t
+torch.cuda.synchronize()
+assert (states[0].packed == states[1].packed).all()
+print("zero-copy parity OK")
