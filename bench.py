@@ -349,7 +349,10 @@ class TTTWL:
         self.local_t = [0] * G
         self.h_actions = [torch.from_numpy(np.random.RandomState(rank + i).randint(0, 27, size=(B,)).astype(np.int8)).pin_memory()
                           for i in range(2)]
-        self.h2d, self.d2h = B, B * 4
+        self.h2d, self.d2h = B, B * 1                  # int8 action up, 1-byte compact record down
+        self.stepper_kwargs = {"compact": True}
+        self.e2e_note = ("host_stepper(compact=True): one graph launch per step = memcpy H2D of the pinned int8 actions + "
+                         "crl_ttt_step + memcpy D2H of the 1-byte records into pinned memory; the host reads a record of every step")
         self.steppers = None
 
     def prepare(self, k0, n):
@@ -361,7 +364,7 @@ class TTTWL:
         self.local_t[g] += 1
 
     def e2e_step(self, k):
-        return _pipelined_e2e_step(self, k, 1)
+        return _pipelined_e2e_step(self, k, 0)
 
     def e2e_drain(self):
         _pipelined_e2e_drain(self)

@@ -198,7 +198,10 @@ ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int
         const int mover = s.mover;
         ttt_step_env<NP>(s, (int)actions[e], o);
         st_stream(out + e, ttt_encode(s));
-        result[e] = ttt_pack_result<NP>(o);
+        if (flags & CRL_FLAG_COMPACT_RESULT)         // 1-byte record: flags | (winner + 1) << 3 | the player who moved << 6
+            ((uint8_t *)result)[e] = (uint8_t)((o.terminal | o.error << 1 | o.placed << 2) | s.winner1 << 3 | mover << 6);
+        else
+            result[e] = ttt_pack_result<NP>(o);
         if (valid_after) valid_after[e] = o.valid_after;
         if (stats) acc.add<NP>(o, mover, s.ep_len);
     }

@@ -6,6 +6,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .base import BatchedBaseEnvironment
+from . import _lib
 
 BOARD_SHAPE = {2: (3, 3), 3: (3, 5), 4: (3, 3, 3)}
 
@@ -83,11 +84,36 @@ class _BatchedTicTacToe(BatchedBaseEnvironment):
                                            self.batch, self.N_PLAYERS, self.flags, self._stream))
         return new
 
-    def host_stepper(self, state: TTTBatchState, stream=None):
+    def host_stepper(self, state: TTTBatchState, stream=None, compact: bool = False):
         """Graph-fused H2D actions -> step -> D2H result for host-side policies (see base.HostStepper).
+        compact=True: the step writes the 1-byte record (CRL_FLAG_COMPACT_RESULT: flags | (winner + 1) << 3 | mover << 6),
+        a quarter of the PCIe read-back; `decode_compact` rebuilds next_state's return values from it on the host.
         NOTE: the warm-up inside applies one step of cell-0 actions to `state`."""
         from .base import HostStepper
-        return HostStepper(self, state, (self.batch,), torch.int8, stream=stream)
+        if not compact:
+            return HostStepper(self, state, (self.batch,), torch.int8, stream=stream)
+        rec = torch.empty((self.batch, 1), dtype=torch.uint8, device=self.device)
+        flags = self.flags | _lib.FLAG_COMPACT_RESULT
+
+        def step(dev_actions):
+            self._check(self._lib.crl_ttt_step(state.packed.data_ptr(), state.packed.data_ptr(), dev_actions.data_ptr(),
+                                               rec.data_ptr(), None, self._stats_ptr, self.batch, self.N_PLAYERS, flags,
+                                               self._stream))
+            state.result = state.valid = None       # the records of an earlier step no longer describe `state`
+            return rec
+        return HostStepper(self, state, (self.batch,), torch.int8, stream=stream, step=step)
+
+    def decode_compact(self, rec):
+        """next_state's return values from 1-byte records (numpy uint8 [B, 1], e.g. HostStepper.wait()):
+        (new_players mask [B], reward int8 [B] (the mover's), terminal [B], winners mask [B]).
+        reward = +1 if the mover is the winner, -1 if somebody else is, else 0 (tictactoe_2p_env.py:302-308)."""
+        import numpy as np
+        r = np.asarray(rec).reshape(-1)
+        terminal, w1, mover = r & 1, (r >> 3) & 7, r >> 6
+        nxt = (mover + 1) % self.N_PLAYERS
+        reward = np.where(w1 == 0, 0, np.where(w1 == mover + 1, 1, -1)).astype(np.int8)
+        winners = np.where(w1 == 0, 0, 1 << np.maximum(w1.astype(np.int32) - 1, 0)).astype(np.uint8)
+        return (1 << nxt).astype(np.uint8), reward, terminal.astype(np.uint8), winners
 
     def valid_actions(self, state: TTTBatchState, player=None) -> torch.Tensor:
         """valid_actions (2p :317-348) as a bit mask: int32 [B], bit c = cell c (C order) is empty; 0 <=> ['']."""

@@ -34,7 +34,8 @@ extern "C" {
 #define CRL_PLAYER_ALL (-3)      /* observe (Tron): the views of all players at once */
 
 #define CRL_FLAG_AUTO_RESET 1 /* an environment whose stored terminal flag is set is replaced by new_state() before the step */
-#define CRL_FLAG_COMPACT_RESULT 2 /* crl_tron_step only: write the 4-byte record (below) instead of the 8-byte one */
+#define CRL_FLAG_COMPACT_RESULT 2 /* crl_tron_step: write the 4-byte record (below) instead of the 8-byte one;
+                                     crl_ttt_step: write the 1-byte record (below) instead of the 4-byte one */
 #define CRL_FLAG_COMPACT2_RESULT 8 /* crl_tron_step only: write the 2-byte record (below) */
 #define CRL_FLAG_PACKED_ACTIONS 4 /* crl_tron_step only: actions are uint8[B], 2 bits per player (action & 3) */
 
@@ -156,7 +157,11 @@ int crl_tron_pack(void *state, const int8_t *board, const int32_t *heads, const 
  * n = 2 (3x3), 3 (3x5), 4 (3x3x3).  Packed state: 16 bytes per environment, uint4[B] (csrc/ttt.cuh).
  * actions: int8[B], C-order flat cell index, negative = '' (pass).
  * result:  4 bytes per environment: int8 reward (mover's) | u8 flags (1 terminal, 2 invalid action, 4 placed) |
- *          u8 winners mask | u8 ranking bits (bit p = rank of p: winners 0, others 1).                      */
+ *          u8 winners mask | u8 ranking bits (bit p = rank of p: winners 0, others 1).
+ *          crl_ttt_step with CRL_FLAG_COMPACT_RESULT: ONE byte per environment = flags (bits 0..2, as above) |
+ *          (winner + 1) << 3 (0 = None) | the player who moved << 6.  Nothing is lost: the mover's reward is +1 if it is
+ *          the winner, -1 if somebody else is, else 0 (tictactoe_2p_env.py:302-308); winners mask and ranking follow from
+ *          the winner; a quarter of the bytes a host-side actor reads back per step.                          */
 int crl_ttt_cells(int n);                                                     /* HOST: 9 / 15 / 27 */
 /* HOST: the winning lines as cell masks (cross-check of WINNING_SHAPES, tictactoe_4p_env.py:19-38); returns count */
 int crl_ttt_lines(int n, uint32_t *line_masks_or_null, int capacity);

@@ -10,7 +10,7 @@ TicTacToe{2,3,4}PlayerEnv) are driven through ``next_state`` / ``valid_actions``
 ``compute_ranking`` / ``state_to_observation`` with Philox4x32-10 action streams and every
 input / output is recorded as plain integer arrays.  These files are the pin for the C oracle
 (tests/test_oracle_golden.py) and are also compared directly with the CUDA engine on the GPU
-(tests/test_gpu_golden.py).  The reference has no tests or golden vectors of its own
+(tests/cases_{tron,ttt,blokus}.py through tests/test_gpu_*.py).  The reference has no tests or golden vectors of its own
 (SURVEY.md section 4), so this is the only pin available.
 """
 import os

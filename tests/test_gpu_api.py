@@ -271,3 +271,28 @@ def test_tron_new_state_spawn_arguments():
     assert (obs["heads"].cpu().numpy()[term] == (h + step[d])[None]).all()
     with pytest.raises(Exception):
         env.new_state(ring_offset=9)                     # no such ring on a 15 x 15 board
+
+
+def test_ttt_compact_host_stepper():
+    """host_stepper(compact=True): 1-byte records whose decode equals next_state's return values, same states."""
+    from colosseumrl_b200.tictactoe import BatchedTicTacToe4PlayerEnv, BatchedTicTacToe2PlayerEnv
+    for cls, cells in ((BatchedTicTacToe4PlayerEnv, 27), (BatchedTicTacToe2PlayerEnv, 9)):
+        B = 700
+        a_env, b_env = cls("", batch=B, seed=2, auto_reset=True), cls("", batch=B, seed=2, auto_reset=True)
+        sa, _ = a_env.new_state()
+        sb, _ = b_env.new_state()
+        stepper = b_env.host_stepper(sb, compact=True)                      # warm-up applies one cell-0 step
+        sa, *_ = a_env.next_state(sa, None, torch.zeros((B,), dtype=torch.int8))
+        rng = np.random.RandomState(3)
+        terminals = wins = 0
+        for t in range(60):
+            a = rng.randint(-1, cells + 1, size=B).astype(np.int8)           # incl. passes, occupied and out-of-range cells
+            sa, pa, ra, ta, wa = a_env.next_state(sa, None, torch.from_numpy(a))
+            stepper.actions_np[...] = a
+            rec = stepper()
+            assert rec.shape == (B, 1)
+            players, reward, terminal, winners = b_env.decode_compact(rec)
+            assert (players == pa.cpu().numpy()).all() and (reward == ra.cpu().numpy()).all()
+            assert (terminal == ta.cpu().numpy()).all() and (winners == wa.cpu().numpy()).all()
+            terminals += int(terminal.sum()); wins += int((winners != 0).sum())
+        assert terminals > 0 and wins > 0 and (sa.packed == sb.packed).all()
