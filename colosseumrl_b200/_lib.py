@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcolosseum_b200.so")
 
 NSTAT = 32
+ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 1, 2, 3     # CRL_ERR_* of include/colosseum_b200.h
 STAT_ROWS = 256
 FLAG_AUTO_RESET = 1
 FLAG_COMPACT_RESULT = 2      # crl_tron_step: 4-byte result record
@@ -26,6 +27,8 @@ SIGNATURES = {
     "crl_init": (_int, [_int]),
     "crl_philox_words": (_int, [_vp, _u64, _u64, _u32, _u32, _i64, _vp]),
     "crl_stats_reduce": (_int, [_vp, _vp, _int, _vp]),
+    "crl_host_graph_launch": (_int, [_vp, _vp, _vp]),
+    "crl_host_event_wait": (_int, [_vp]),
     "crl_tron_state_bytes": (_i64, [_int, _int, _i64]),
     "crl_tron_action_stride": (_int, [_int, _int]),
     "crl_tron_result_bytes": (_int, [_int, _int]),

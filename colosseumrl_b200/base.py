@@ -85,6 +85,9 @@ class HostStepper:
         self._done = _cudart.new_event()
         self._stream_handle = s.cuda_stream
         _cudart.check(self._rt.cudaGraphUpload(self._exec, self._stream_handle), "cudaGraphUpload")
+        # ONE foreign call per launch (graph launch + event record) and one per wait: libcolosseum_b200's host helpers
+        raw = _lib.load()
+        self._launch_fn, self._wait_fn = raw.crl_host_graph_launch, raw.crl_host_event_wait
 
     def _build(self, env, state, action_shape, action_dtype, stream, step):
         self.actions = torch.zeros(action_shape, dtype=action_dtype).pin_memory()
@@ -108,25 +111,22 @@ class HostStepper:
         self._finish(env, stream if stream is not None else torch.cuda.current_stream(env.device))
 
     def launch(self):
-        """Enqueue H2D + step + D2H (one graph launch) on the stepper's stream; returns immediately."""
-        rc = self._rt.cudaGraphLaunch(self._exec, self._stream_handle) or self._rt.cudaEventRecord(self._done, self._stream_handle)
-        if rc == 400:
-            # cudaErrorInvalidResourceHandle: the calling thread's current device is not the stepper's.  The hot loop of a
-            # one-process-per-GPU actor never pays for a device guard; a multi-device process lands here and retries
-            # under one (the failed call launched nothing).
-            self._rt.cudaGetLastError()
-            with torch.cuda.device(self.env.device):
-                rc = self._rt.cudaGraphLaunch(self._exec, self._stream_handle) or \
-                    self._rt.cudaEventRecord(self._done, self._stream_handle)
+        """Enqueue the step (one graph launch) on the stepper's stream; returns immediately."""
+        rc = self._launch_fn(self._exec, self._stream_handle, self._done)
         if rc:
-            raise RuntimeError("HostStepper launch failed: cudaError %d" % rc)
+            if rc == _lib.ERR_ARG:
+                # the calling thread's current device is not the stepper's.  The hot loop of a one-process-per-GPU actor
+                # never pays for a device guard; a multi-device process lands here and retries under one (the failed
+                # call launched nothing).
+                with torch.cuda.device(self.env.device):
+                    rc = self._launch_fn(self._exec, self._stream_handle, self._done)
+            if rc:
+                raise RuntimeError("HostStepper launch failed: %s" % _lib.load().crl_last_error().decode())
 
     def wait(self):
-        """Block until the launched step's result record is in `self.result` (pinned host memory).  (Waiting for the
-        stepper's stream instead of an event saves a runtime call per step but measured no faster end to end.)"""
-        rc = self._rt.cudaEventSynchronize(self._done)
-        if rc:
-            raise RuntimeError("HostStepper wait failed: cudaError %d" % rc)
+        """Block until the launched step's result record is in `self.result` (pinned host memory)."""
+        if self._wait_fn(self._done):
+            raise RuntimeError("HostStepper wait failed: %s" % _lib.load().crl_last_error().decode())
         return self.result_np
 
     def __del__(self):

@@ -72,6 +72,37 @@ int crl_stats_reduce(const int64_t *stats_rows, int64_t *out, int accumulate, cr
     return check_launch("stats_reduce_kernel");
 }
 
+/* Host-side helpers of the host-policy step loop (colosseumrl_b200/base.py::HostStepper): ONE foreign call per
+ * launch (graph launch + completion-event record) and one per wait.  The loop is bound by the host's per-step cost, and a
+ * ctypes call costs as much as the runtime call it wraps. */
+int crl_host_graph_launch(void *graph_exec, crl_stream_t stream, void *done_event) {
+#ifndef CRL_HOSTSIM
+    cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream);
+    if (e == cudaSuccess && done_event) e = cudaEventRecord((cudaEvent_t)done_event, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        snprintf(g_err, sizeof(g_err), "crl_host_graph_launch: %s", cudaGetErrorString(e));
+        return e == cudaErrorInvalidResourceHandle ? CRL_ERR_ARG : CRL_ERR_CUDA;
+    }
+    return CRL_OK;
+#else
+    return fail(CRL_ERR_UNSUPPORTED, "crl_host_graph_launch: no CUDA runtime in the emulator build%s");
+#endif
+}
+
+int crl_host_event_wait(void *event) {
+#ifndef CRL_HOSTSIM
+    cudaError_t e = cudaEventSynchronize((cudaEvent_t)event);
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "crl_host_event_wait: %s", cudaGetErrorString(e));
+        return CRL_ERR_CUDA;
+    }
+    return CRL_OK;
+#else
+    return fail(CRL_ERR_UNSUPPORTED, "crl_host_event_wait: no CUDA runtime in the emulator build%s");
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------- Tron */
 
 static int tron_check(int N, int P, int64_t B) {

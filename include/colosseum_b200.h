@@ -73,6 +73,13 @@ int crl_philox_words(uint32_t *out, uint64_t seed, uint64_t first_env, uint32_t 
  * the reference has no counterpart: its statistics are Python-side counters in the callers' loops). */
 int crl_stats_reduce(const int64_t *stats_rows, int64_t *out, int accumulate, crl_stream_t stream);
 
+/* HOST helpers for actors whose policy runs on the host (match_server.py:201-218: actions arrive on the host, results
+ * go back to it): launch a captured step graph (cudaGraphExec_t) on `stream` and record `done_event` (cudaEvent_t, may
+ * be NULL) behind it in ONE foreign call; block until an event has completed.  CRL_ERR_ARG = the calling thread's
+ * current device does not own the handles (nothing was launched; retry under a device guard). */
+int crl_host_graph_launch(void *graph_exec, crl_stream_t stream, void *done_event_or_null);
+int crl_host_event_wait(void *event);
+
 /* ------------------------------------------------------------------------------------------- Tron
  * Any shape the reference's config string can name within 5 <= N <= 64, 2 <= P <= 8 (TronGridEnvironment.py:28-58;
  * CyTronGrid.pyx:8-9 takes N and P from the array shapes).  Two state layouts, chosen by the shape alone:
