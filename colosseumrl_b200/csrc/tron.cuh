@@ -416,6 +416,11 @@ tron_step_kernel(const __grid_constant__ TronMaps maps, const uint4 *__restrict_
             a = actions[e0 + t];
         }
     }
+#ifndef CRL_HOSTSIM
+    // (diagnostic 0x8000 / 0x10000: stagger the tile loads of the CTAs that share an SM by 100 / 200 ns per rank, to see
+    // whether a launch's load and store phases can be made to overlap)
+    if ((flags & 0x18000) && t == 0) __nanosleep((blockIdx.x / 148u) * ((flags & 0x8000) ? 100u : 0u) + (blockIdx.x / 148u) * ((flags & 0x10000) ? 200u : 0u));
+#endif
     tron_tile_load_issue(tile, bar, &maps, in, B, e0, n);
     TronOut o;
     tron_zero_out(o);

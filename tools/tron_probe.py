@@ -16,7 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from colosseumrl_b200.tron import BatchedTronGridEnvironment  # noqa: E402
 
-VARIANTS = [("full", 0), ("full, PDL trigger at the very top", 0x4000), ("full, late PDL trigger", 0x1000), ("full, no L2 prefetch", 0x2000),
+VARIANTS = [("full", 0), ("full, loads staggered 100 ns / SM rank", 0x8000), ("full, loads staggered 200 ns / SM rank", 0x10000),
+            ("full, loads staggered 300 ns / SM rank", 0x18000),
+            ("data movement only, staggered 200 ns", 0x100 | 0x800 | 0x10000), ("full, PDL trigger at the very top", 0x4000), ("full, late PDL trigger", 0x1000), ("full, no L2 prefetch", 0x2000),
             ("full, round-1 (late trigger, no prefetch)", 0x3000),
             ("no stats", 0x800), ("no phase3, no stats", 0xC00), ("no phase2/3, no stats", 0xE00),
             ("data movement only", 0x100 | 0x800), ("data movement only, round-1", 0x100 | 0x800 | 0x3000),
