@@ -159,12 +159,15 @@ struct TTTStatAcc {
     __device__ __forceinline__ void flush(int *sm_stat, uint32_t lane_const) {
         const uint32_t a = __reduce_add_sync(0xffffffffu, A), w = __reduce_add_sync(0xffffffffu, W);
         const uint32_t d = __reduce_add_sync(0xffffffffu, D), r = __reduce_add_sync(0xffffffffu, R);
-        const uint32_t word = lane_const & 15u;
-        const uint32_t x = word == 0u ? a : word == 1u ? w : word == 2u ? d : r;
+        // branch-free: the word by two selects on its two index bits, the field by shift + mask, the two derived kinds
+        // by selects (the first version compiled to a chain of branches around moves)
+        const uint32_t lo = (lane_const & 1u) ? w : a, hi = (lane_const & 1u) ? r : d;
+        const uint32_t x = (lane_const & 2u) ? hi : lo;
         int val = (int)((x >> ((lane_const >> 4) & 31u)) & ((1u << ((lane_const >> 10) & 31u)) - 1u));
         const uint32_t kind = lane_const >> 24;
-        if (kind == 1u) val = ((lane_const >> 7) & 7u) < (uint32_t)NP ? (int)((a >> 8) & 255u) - val : 0;   // not-a-winner, seats < NP
-        if (kind == 2u) val -= 4 * (int)(a & 255u);                         // remove the reward bias
+        const int notwin = ((lane_const >> 7) & 7u) < (uint32_t)NP ? (int)((a >> 8) & 255u) - val : 0;       // not-a-winner, seats < NP
+        val = kind == 1u ? notwin : val;
+        val -= kind == 2u ? 4 * (int)(a & 255u) : 0;                        // remove the reward bias
         const int slot = (int)((lane_const >> 16) & 255u);
         if ((int)(threadIdx.x & 31) < TTT_STAT_LANES && val != 0) atomicAdd(&sm_stat[slot], val);
         clear();
