@@ -27,7 +27,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "crl_api.cu")]
+    extra = os.environ.get("CRL_NVCC_EXTRA", "").split()          # e.g. -DTTT_DBG=7 for a timing-attribution build
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB, os.path.join(CSRC, "crl_api.cu")]
     env = dict(os.environ)
     # nvcc's host compiler must be the system g++ (the image's CC/CXX wrappers lack some spec files)
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)

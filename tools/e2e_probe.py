@@ -123,3 +123,35 @@ for t in range(20):
 torch.cuda.synchronize()
 assert (states[0].packed == states[1].packed).all()
 print("zero-copy parity OK")
+
+
+def run_threads(name, nthreads, depth):
+    """`nthreads` host threads, each driving its own share of the zero-copy steppers (ctypes releases the GIL during the
+    runtime calls): does the host-bound leg scale with actor threads?"""
+    import threading
+    sps = [envs[i].host_stepper(states[i], stream=torch.cuda.Stream(), compact=2, packed_actions=True, zero_copy=True) for i in range(G)]
+    for sp in sps: sp()
+    torch.cuda.synchronize()
+    per = K // nthreads
+
+    def worker(mine):
+        launch = [sp.launch for sp in mine]; wait = [sp.wait for sp in mine]
+        n = len(mine); r = 0
+        for k in range(per):
+            launch[k % n]()
+            j = k - depth + 1
+            if j >= 0: r += int(wait[j % n]()[0, 0])
+        for j in range(max(0, per - depth + 1), per): r += int(wait[j % n]()[0, 0])
+
+    ths = [threading.Thread(target=worker, args=(sps[t::nthreads],)) for t in range(nthreads)]
+    t0 = time.perf_counter()
+    for t in ths: t.start()
+    for t in ths: t.join()
+    dt = time.perf_counter() - t0
+    print("%-34s %.2f us/step  %.2f G env-steps/s" % (name, dt / (per * nthreads) * 1e6, B * per * nthreads / dt / 1e9))
+
+
+K = 4000
+run_threads("zero-copy, 1 thread, depth 16", 1, 16)
+run_threads("zero-copy, 2 threads, depth 8 each", 2, 8)
+run_threads("zero-copy, 4 threads, depth 4 each", 4, 4)
