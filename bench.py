@@ -381,12 +381,31 @@ class TTTWL:
                          "crl_ttt_step + memcpy D2H of the 1-byte records into pinned memory; the host reads a record of every step")
         self.steppers = None
 
+    mode = "fused"          # "next_state": crl_ttt_step with resident, pre-recorded actions (secondary figure)
+
     def prepare(self, k0, n):
-        pass
+        """next_state mode: the actions of steps k0..k0+n-1 depend on the states, so the steps are played once for real
+        (policy kernel + step), their actions recorded, and the states put back -- outside the timed region."""
+        if self.mode != "next_state":
+            return
+        torch = self.torch
+        snap = [s.packed.clone() for s in self.states]
+        self.actions = torch.empty((n, self.B), dtype=torch.int8, device=snap[0].device)
+        lt = list(self.local_t)
+        for j in range(n):
+            g = (k0 + j) % self.G
+            self.envs[g].random_actions(self.states[g], lt[g], out=self.actions[j])
+            self.envs[g].step_(self.states[g], self.actions[j], out=self.states[g])
+            lt[g] += 1
+        for s_, c in zip(self.states, snap):
+            s_.packed.copy_(c)
 
     def step(self, k, slot=None):
         g = k % self.G
-        self.envs[g].rollout(self.states[g], self.local_t[g], 1)      # policy (in-kernel Philox) + step, one launch
+        if self.mode == "next_state" and slot is not None:
+            self.envs[g].step_(self.states[g], self.actions[slot], out=self.states[g])      # crl_ttt_step, one launch
+        else:
+            self.envs[g].rollout(self.states[g], self.local_t[g], 1)  # policy (in-kernel Philox) + step, one launch
         self.local_t[g] += 1
 
     def e2e_step(self, k):
@@ -698,6 +717,21 @@ def measure_b200(name, args, cx, with_cpu):
     step_ms = steps_ms_max / n_timed
     launch_ms = step_ms / wl["launches"]
 
+    # ---- TTT only: next_state alone (crl_ttt_step with resident, pre-recorded actions) next to the fused policy + step
+    next_state_only = None
+    if name == "ttt4" and not args.no_e2e:
+        work.mode = "next_state"
+        n2 = min(n_timed, 1024)
+        g2 = capture(k, n2, S)
+        (t2,) = cx.max_over_ranks([timed_replay(g2) / n2])
+        k += n2
+        del g2
+        work.mode, work.actions = "fused", None
+        next_state_only = {"ms_per_step": t2, "steps": n2, "algorithmic_bytes_per_env_step": 41,
+                           "note": "crl_ttt_step (next_state + fused valid-after mask) with resident actions recorded from the "
+                                   "same random policy; 16 + 16 + 1 + 4 + 4 B per env-step"}
+        work.stats_env.stats_rows.zero_()
+
     # ---- end to end through the public API with host buffers: K x Re steps (>= --min-ms)
     if args.no_e2e:
         work.e2e_run = lambda k_, n_: 0
@@ -738,6 +772,9 @@ def measure_b200(name, args, cx, with_cpu):
                {"ms_per_step": serial, "frac": bytes_per_step * B / (serial * 1e-3) / 1e9 / peak,
                 "note": "same steps as one dependent chain (every launch waits for its predecessor, PDL only)"}}
         roofline = hbm
+        if next_state_only is not None:
+            next_state_only["frac"] = 41 * B / (next_state_only["ms_per_step"] * 1e-3) / 1e9 / peak
+            hbm["next_state_only"] = next_state_only
         if name == "blokus":
             issue = issue_roofline(args, stats, step_ms, clk)
             if issue is not None:

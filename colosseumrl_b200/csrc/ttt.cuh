@@ -132,6 +132,16 @@ __device__ __forceinline__ uint32_t ttt_pack_result(const TTTOut &o) {
 #ifndef TTT_DBG
 #define TTT_DBG 0
 #endif
+// where a warp's statistics sums go: 1 = straight to the CTA's row of the global buffer (fire-and-forget RED.64, no
+// shared partial, no barriers), 0 = a shared partial per CTA + two barriers + one flush per CTA (round 1).  Measured
+// (us per 1,048,576-env step, 4 chains / 1 chain): next_state 6.92 / 9.65 against 7.85 / 11.59 -> global; fused rollout
+// 8.88 / 13.79 against 8.97 / 12.65 -> shared (its flush sits before the state store of the last step)
+#ifndef TTT_STATS_GLOBAL_STEP
+#define TTT_STATS_GLOBAL_STEP 1
+#endif
+#ifndef TTT_STATS_GLOBAL_ROLLOUT
+#define TTT_STATS_GLOBAL_ROLLOUT 0
+#endif
 #define TTT_ROLLOUT_MINB 8     // default register budget of the fused rollout kernel (see its template parameter)
 #define TTT_SL(word, shift, bits, slot, kind) ((word) | (shift) << 4 | (bits) << 10 | (slot) << 16 | (kind) << 24)
 __constant__ uint32_t TTT_STAT_LANE[32] = {
@@ -158,8 +168,8 @@ struct TTTStatAcc {
         R += (uint32_t)((mover + 1) * o.reward + 4);
     }
     // warp-collective: reduce, extract, add to the CTA's shared partial, clear
-    template <int NP>
-    __device__ __forceinline__ void flush(int *sm_stat, uint32_t lane_const) {
+    template <int NP, bool GLOBAL>
+    __device__ __forceinline__ void flush(int *sm_stat, uint32_t lane_const, crl_u64 *row) {
         const uint32_t a = __reduce_add_sync(0xffffffffu, A), w = __reduce_add_sync(0xffffffffu, W);
         const uint32_t d = __reduce_add_sync(0xffffffffu, D), r = __reduce_add_sync(0xffffffffu, R);
 #ifndef TTT_FLUSH_BRANCHY
@@ -181,7 +191,10 @@ struct TTTStatAcc {
         if (kind == 2u) val -= 4 * (int)(a & 255u);
 #endif
         const int slot = (int)((lane_const >> 16) & 255u);
-        if ((int)(threadIdx.x & 31) < TTT_STAT_LANES && val != 0) atomicAdd(&sm_stat[slot], val);
+        if ((int)(threadIdx.x & 31) < TTT_STAT_LANES && val != 0) {
+            if (GLOBAL) atomicAdd(&row[slot], (crl_u64)(long long)val);
+            else atomicAdd(&sm_stat[slot], val);
+        }
         clear();
     }
 };
@@ -197,7 +210,8 @@ ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int
                 uint32_t *__restrict__ result, uint32_t *__restrict__ valid_after, crl_u64 *stats, long long B,
                 int flags) {
     __shared__ int sm_stat[CRL_NSTAT];
-    if (stats) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
+    if (stats && !TTT_STATS_GLOBAL_STEP) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
+    crl_u64 *const row = stats ? stats + (blockIdx.x & (CRL_STAT_ROWS - 1)) * CRL_NSTAT : nullptr;
     TTTStatAcc acc;
     acc.clear();
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -221,9 +235,11 @@ ttt_step_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, const int
         if (stats) acc.add<NP>(o, mover, s.ep_len);
     }
     if (stats) {
-        acc.flush<NP>(sm_stat, TTT_STAT_LANE[threadIdx.x & 31]);
-        __syncthreads();
-        stats_flush_row(sm_stat, stats);
+        acc.flush<NP, TTT_STATS_GLOBAL_STEP != 0>(sm_stat, TTT_STAT_LANE[threadIdx.x & 31], row);
+        if (!TTT_STATS_GLOBAL_STEP) {
+            __syncthreads();
+            stats_flush_row(sm_stat, stats);
+        }
     }
 }
 
@@ -365,7 +381,8 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
     constexpr int dbg = TTT_DBG;
     constexpr uint32_t CM = TTTGeo<NP>::CELLMASK;
     __shared__ int sm_stat[CRL_NSTAT];
-    if (STATS) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
+    if (STATS && !TTT_STATS_GLOBAL_ROLLOUT) { if (threadIdx.x < CRL_NSTAT) sm_stat[threadIdx.x] = 0; __syncthreads(); }
+    crl_u64 *const row = STATS ? stats + (blockIdx.x & (CRL_STAT_ROWS - 1)) * CRL_NSTAT : nullptr;
     const uint32_t lane_const = TTT_STAT_LANE[threadIdx.x & 31], rcp_lane = ttt_rcp_lane();
     TTTStatAcc acc;
     acc.clear();
@@ -393,7 +410,7 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
                 if (valid && !(dbg & 1)) ttt_fused_stats(acc, o);
                 if (++pending == TTT_ACC_MAX && !(dbg & 2)) {
                     acc.bias_from_steps();
-                    acc.flush<NP>(sm_stat, lane_const);
+                    acc.flush<NP, TTT_STATS_GLOBAL_ROLLOUT != 0>(sm_stat, lane_const, row);
                     pending = 0;
                 }
             }
@@ -404,9 +421,11 @@ ttt_rollout_kernel(uint4 *__restrict__ state, uint32_t *__restrict__ result, crl
         }
     }
     if (STATS && !(dbg & 4)) {
-        if (pending && !(dbg & 2)) { acc.bias_from_steps(); acc.flush<NP>(sm_stat, lane_const); }
-        __syncthreads();
-        stats_flush_row(sm_stat, stats);
+        if (pending && !(dbg & 2)) { acc.bias_from_steps(); acc.flush<NP, TTT_STATS_GLOBAL_ROLLOUT != 0>(sm_stat, lane_const, row); }
+        if (!TTT_STATS_GLOBAL_ROLLOUT) {
+            __syncthreads();
+            stats_flush_row(sm_stat, stats);
+        }
     }
 }
 
