@@ -607,9 +607,12 @@ tron_observe_kernel(const uint4 *__restrict__ st, long long B, TronParams prm, i
         const uint32_t *wp = tile.words(t) + wl;
         uint8_t *out = img + t * nview * NN + 4 * lane;
         for (int k = 0; k < chunks; k++, wp += TRON_OBS_TILE * 4, out += 128) {
-            uint32_t ow = 0;                                 // owner of the lane's 4 cells, one byte each
-#pragma unroll
-            for (int q = 0; q < 4; q++) ow += ((((wp[q * PL] >> sh) & 15u) * 0x00204081u) & TRON_ONES) * (uint32_t)(q + 1);
+            // owner (0 empty, q + 1) of the lane's 4 cells, one byte each: the planes are disjoint, so the three BIT-PLANES of
+            // the owner value are p0 | p2, p1 | p2 and p3 -- three nibble -> bytes spreads instead of four
+            const uint32_t p0 = wp[0], p1 = wp[PL], p2 = wp[2 * PL], p3 = wp[3 * PL];
+            const uint32_t v0 = ((p0 | p2) >> sh) & 15u, v1 = ((p1 | p2) >> sh) & 15u, v2 = (p3 >> sh) & 15u;
+            const uint32_t ow = ((v0 * 0x00204081u) & TRON_ONES) + 2u * ((v1 * 0x00204081u) & TRON_ONES) +
+                                4u * ((v2 * 0x00204081u) & TRON_ONES);
             const uint32_t sel = __byte_perm(ow | ow >> 4, 0u, 0x4420);      // the 4 owners as PRMT selector nibbles
             const int c0 = 128 * k + 4 * lane;
             const bool guard = k == chunks - 1;
@@ -621,18 +624,26 @@ tron_observe_kernel(const uint4 *__restrict__ st, long long B, TronParams prm, i
                 tron_obs_store4(out, __byte_perm(lut_lo[0], lut_hi[0], sel), c0, NN, guard);
             }
         }
-        if (lane < nview * P) {                                            // per-player vectors, rolled by the viewer (py:392-396)
-            const long long e = e0 + t;
-            const int pv = ALL ? lane / P : max(player, 0), c = ALL ? lane - pv * P : lane;
+    }
+    // per-player vectors, rolled by the viewer (py:392-396): ONE pass over the tile -- thread i owns entry i of the
+    // tile's [env][view][player] block, which is contiguous in the three output arrays (coalesced 4-byte stores).  (Done
+    // per environment by the lanes of its warp, as at first, this part was 93 of the kernel's 264 warp instructions per
+    // environment: integer divisions and 64-bit index arithmetic for 4..16 useful lanes.)
+    {
+        const int per_env = nview * P, entries = n * per_env;
+        for (int i = threadIdx.x; i < entries; i += blockDim.x) {
+            const int t = i / per_env, r = i - t * per_env;
+            const int pv = ALL ? r / P : max(player, 0), c = ALL ? r - pv * P : r;
+            int src = c + ((!ALL && player == -1) ? 0 : pv);
+            src -= src >= P ? P : 0;
             const uint4 h = tile.v[12][t];
-            const int src = (!ALL && player == -1) ? c : (c + pv) % P;
             const uint32_t bx = (h.x >> (8 * src)) & 255u, by = (h.y >> (8 * src)) & 255u;
-            const long long o = (e * nview + (ALL ? pv : 0)) * P + c;
+            const long long o = e0 * per_env + i;
             if (heads) heads[o] = ((int)(by & 31u) - 1) * N + (int)(bx & 31u) - 1;
             if (dirs) dirs[o] = (int)(bx >> 5) & 3;
             if (deaths) deaths[o] = (int)(by >> 5);
-            if (terminal && lane == 0) terminal[e] = (uint8_t)((h.z >> 27) & 1u);
         }
+        if (terminal && (int)threadIdx.x < n) terminal[e0 + threadIdx.x] = (uint8_t)((tile.v[12][threadIdx.x].z >> 27) & 1u);
     }
     // the tile's boards: one bulk copy when the segment is 16-byte aligned and sized, a cooperative byte copy otherwise
     const int nbytes = n * nview * NN;
