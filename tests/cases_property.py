@@ -140,7 +140,7 @@ def blokus_property(be, examples):
         sst = cb.blk_pack(be, boards, inv, scores, rounds, movers)
         lists = {}
         for p in range(4):
-            counts, ids = cb.blk_legal(be, sst, player=p, cap=4096)
+            counts, ids = cb.blk_legal(be, sst, player=p, cap=16384)     # (generated boards reach > 4 096 moves)
             for i in range(n):
                 exp = orc.blokus_valid_moves((boards[i].astype(np.int64), int(rounds[i]), inv[i], scores[i]), p, cap=16384)
                 assert counts[i] == len(exp) and (ids[i, :len(exp)] == exp).all()
