@@ -299,18 +299,47 @@ class _TicTacToe(SingleEnvironment):
             raise ValueError("bad Tic Tac Toe action %r" % (action,))
         return int(np.ravel_multi_index(idx, self._shape))
 
+    # The step kernel already produces everything the NEXT calls need (the packed state and its valid-action mask), so
+    # the adapter remembers them for the state object it returns: `valid_actions(state)` on it costs no GPU work and
+    # `next_state(state, ...)` no re-pack -- one host round trip per game step (H2D action, step kernel, one D2H) instead
+    # of four.  The memo is checked by CONTENT (board bytes, winner, mover), so a caller that edits a state still gets
+    # the right answer (it just pays for the pack again).
+    _memo = None
+
+    def _lookup(self, state, mover: int):
+        m = self._memo
+        if m is not None and m[2] == mover and m[1] == state[1] and m[0] == np.asarray(state[0], np.int8).tobytes():
+            return m
+        return None
+
+    def _packed(self, state, mover: int):
+        m = self._lookup(state, mover)
+        return m[3] if m is not None else self._pack(state, mover)
+
     def next_state(self, state, players: List[int], actions: List[str]):
-        mover = int(players[0])
-        new = self._b.step_(self._pack(state, mover), torch.tensor([self._index(actions[0])], dtype=torch.int8))
-        board, winner, _ = (self._np(x) for x in self._b.state_arrays(new))
-        r = self._np(new.result[0])
-        w = None if winner[0] < 0 else int(winner[0])
+        mover, n = int(players[0]), self.max_players
+        new = self._b.step_(self._packed(state, mover), torch.tensor([self._index(actions[0])], dtype=torch.int8))
+        # ONE device -> host read: packed state (16 B) | result record (4 B) | valid-after mask (4 B)
+        raw = torch.cat([new.packed.view(torch.uint8).reshape(-1), new.result.reshape(-1),
+                         new.valid.view(torch.uint8).reshape(-1)]).cpu().numpy()
+        words, r, mask = raw[:16].view(np.uint32), raw[16:20], int(raw[20:24].view(np.uint32)[0])
+        nmover, w1 = int(words[0] >> 27) & 3, int(words[0] >> 29)
+        board = np.full(int(np.prod(self._shape)), -1, np.int8)
+        for p in range(n):                         # mover-relative layout (csrc/ttt.cuh): word j = player (mover + j) % n
+            cells = int(words[(p - nmover) % n]) & 0x07ffffff
+            while cells:
+                c = (cells & -cells).bit_length() - 1
+                board[c] = p
+                cells &= cells - 1
+        w = None if w1 == 0 else w1 - 1
+        out = (board.reshape(self._shape), w)
+        self._memo = (board.tobytes(), w, nmover, new, mask)
         terminal = bool(r[1] & 1)
-        winners = [w] if w is not None else None
-        return (board[0].reshape(self._shape).astype(np.int8), w), [(mover + 1) % self.max_players], [int(np.int8(r[0]))], terminal, winners
+        return out, [(mover + 1) % n], [int(np.int8(r[0]))], terminal, ([w] if w is not None else None)
 
     def valid_actions(self, state, player: int) -> List[str]:
-        mask = int(self._b.valid_actions(self._pack(state, player))[0])
+        m = self._lookup(state, int(player))
+        mask = m[4] if m is not None else int(self._b.valid_actions(self._pack(state, player))[0])
         cells = [c for c in range(int(np.prod(self._shape))) if mask >> c & 1]
         if not cells:
             return [""]
