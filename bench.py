@@ -853,11 +853,12 @@ def measure_ttt2(args, cx):
             "warmup": args.warmup, "reps": 1, "timed_steps": n, "ms_per_step": dt / n * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config_of("ttt2", 1),
             "method": {"note": "single-environment string-action adapter (colosseumrl_b200.single): valid_actions + "
-                               "next_state per step, each a host round trip; wall-clock timed (launch-latency-bound)"},
+                               "next_state per step = one host round trip (H2D action, crl_ttt_step, one D2H; the valid "
+                               "list comes from the step's fused valid-after mask); wall-clock timed (launch-latency-bound)"},
             "roofline": None,
-            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 9 + 2, "d2h_bytes_per_step": 9 + 2 + 4,
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 1, "d2h_bytes_per_step": 24,
                     "steps": n},
-            "gpu_launches": 4 * n,
+            "gpu_launches": n,          # one crl_ttt_step per game step (+ a pack / valid launch at every episode start)
             "cpu_baseline": cpu_baseline("ttt2", target_s=2.0) if cx.world == 1 and not args.no_cpu else None}
 
 
