@@ -291,15 +291,17 @@ def _pipelined_e2e_run(work, k0, n, probe_col):
         _pipelined_e2e_drain(work)
         k0, n = k0 + 1, n - 1
     G, D = work.G, E2E_DEPTH
-    launch = [sp.launch for sp in work.steppers]
-    wait = [sp.wait for sp in work.steppers]
+    sps = work.steppers
+    launch = [sp.launch for sp in sps]
+    step = [sp.launch_then_wait for sp in sps]                    # launch batch k, wait for batch k - D + 1: one foreign call
+    wait = [sp.wait for sp in sps]
     r = 0
-    for k in range(k0, k0 + n):
+    fill = min(n, D - 1)
+    for k in range(k0, k0 + fill):                                # fill the pipeline
         launch[k % G]()
-        j = k - D + 1
-        if j >= k0:
-            r += int(wait[j % G]()[0, probe_col])                 # the host reads the result record (numpy view, pinned)
-    for j in range(max(k0, k0 + n - D + 1), k0 + n):
+    for k in range(k0 + fill, k0 + n):
+        r += int(step[k % G](sps[(k - D + 1) % G])[0, probe_col])  # the host reads the result record (numpy view, pinned)
+    for j in range(max(k0, k0 + n - D + 1), k0 + n):              # drain
         r += int(wait[j % G]()[0, probe_col])
     return r
 

@@ -28,6 +28,7 @@ SIGNATURES = {
     "crl_philox_words": (_int, [_vp, _u64, _u64, _u32, _u32, _i64, _vp]),
     "crl_stats_reduce": (_int, [_vp, _vp, _int, _vp]),
     "crl_host_graph_launch": (_int, [_vp, _vp, _vp]),
+    "crl_host_graph_launch_wait": (_int, [_vp, _vp, _vp, _vp]),
     "crl_host_event_wait": (_int, [_vp]),
     "crl_tron_state_bytes": (_i64, [_int, _int, _i64]),
     "crl_tron_action_stride": (_int, [_int, _int]),

@@ -88,6 +88,7 @@ class HostStepper:
         # ONE foreign call per launch (graph launch + event record) and one per wait: libcolosseum_b200's host helpers
         raw = _lib.load()
         self._launch_fn, self._wait_fn = raw.crl_host_graph_launch, raw.crl_host_event_wait
+        self._launch_wait_fn = raw.crl_host_graph_launch_wait
 
     def _build(self, env, state, action_shape, action_dtype, stream, step):
         self.actions = torch.zeros(action_shape, dtype=action_dtype).pin_memory()
@@ -122,6 +123,18 @@ class HostStepper:
                     rc = self._launch_fn(self._exec, self._stream_handle, self._done)
             if rc:
                 raise RuntimeError("HostStepper launch failed: %s" % _lib.load().crl_last_error().decode())
+
+    def launch_then_wait(self, oldest: "HostStepper"):
+        """A pipelined actor's whole step in ONE foreign call: enqueue this batch's step, then block until the step of
+        `oldest` (the batch launched longest ago) has delivered its records; returns `oldest.result_np`."""
+        rc = self._launch_wait_fn(self._exec, self._stream_handle, self._done, oldest._done)
+        if rc:
+            if rc == _lib.ERR_ARG:                 # wrong current device: retry under a guard (nothing was launched)
+                with torch.cuda.device(self.env.device):
+                    rc = self._launch_wait_fn(self._exec, self._stream_handle, self._done, oldest._done)
+            if rc:
+                raise RuntimeError("HostStepper launch failed: %s" % _lib.load().crl_last_error().decode())
+        return oldest.result_np
 
     def wait(self):
         """Block until the launched step's result record is in `self.result` (pinned host memory)."""

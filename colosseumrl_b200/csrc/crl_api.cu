@@ -90,6 +90,21 @@ int crl_host_graph_launch(void *graph_exec, crl_stream_t stream, void *done_even
 #endif
 }
 
+int crl_host_graph_launch_wait(void *graph_exec, crl_stream_t stream, void *done_event, void *wait_event) {
+#ifndef CRL_HOSTSIM
+    int rc = crl_host_graph_launch(graph_exec, stream, done_event);
+    if (rc || !wait_event) return rc;
+    cudaError_t e = cudaEventSynchronize((cudaEvent_t)wait_event);
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "crl_host_graph_launch_wait: %s", cudaGetErrorString(e));
+        return CRL_ERR_CUDA;
+    }
+    return CRL_OK;
+#else
+    return fail(CRL_ERR_UNSUPPORTED, "crl_host_graph_launch_wait: no CUDA runtime in the emulator build%s");
+#endif
+}
+
 int crl_host_event_wait(void *event) {
 #ifndef CRL_HOSTSIM
     cudaError_t e = cudaEventSynchronize((cudaEvent_t)event);

@@ -78,6 +78,9 @@ int crl_stats_reduce(const int64_t *stats_rows, int64_t *out, int accumulate, cr
  * be NULL) behind it in ONE foreign call; block until an event has completed.  CRL_ERR_ARG = the calling thread's
  * current device does not own the handles (nothing was launched; retry under a device guard). */
 int crl_host_graph_launch(void *graph_exec, crl_stream_t stream, void *done_event_or_null);
+/* the pipelined actor's whole step in one foreign call: launch this batch's step, then block until `wait_event` (the
+ * completion event of the OLDEST batch in flight, may be NULL) has completed */
+int crl_host_graph_launch_wait(void *graph_exec, crl_stream_t stream, void *done_event_or_null, void *wait_event_or_null);
 int crl_host_event_wait(void *event);
 
 /* ------------------------------------------------------------------------------------------- Tron

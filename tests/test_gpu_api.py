@@ -211,7 +211,7 @@ def test_compact_host_stepper(compact):
         a = rng.randint(-1, 2, size=(B, 4)).astype(np.int8)
         sa, pa, ra, ta, wa = a_env.next_state(sa, None, torch.from_numpy(a))
         stepper.actions_np[...] = b_env.pack_actions(a)
-        rec = stepper()
+        rec = stepper() if t % 2 == 0 else stepper.launch_then_wait(stepper)      # (one foreign call: launch + wait)
         assert rec.shape == (B, 2 if compact == 2 else 4) and stepper.actions_np.shape == (B,)
         alive, rewards, terminal, winners, ranking = b_env.decode_compact(rec)
         assert (alive == pa.cpu().numpy()).all() and (rewards == ra.cpu().numpy()).all()
