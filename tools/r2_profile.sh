@@ -33,7 +33,9 @@ $NCU --set full --import-source on --profile-from-start off -k regex:blokus_lega
 $NCU --set full --import-source on --profile-from-start off -k regex:blokus_step -s 100 -c 1 -o $out/prof_blokus_step_$tag -f \
     python bench.py --workload blokus --steps 20 --warmup 5 --no-cpu --no-e2e --reps 8 --profile-range > $out/full_blokus_step_$tag.log 2>&1
 python tools/observe_probe.py > $out/observe_probe_$tag.log 2>&1 && \
-$NCU --set full --import-source on -k regex:observe -c 5 -o $out/prof_observe_$tag -f python tools/observe_probe.py > $out/full_observe_$tag.log 2>&1
+for k in tron_observe blokus_observe ttt_observe; do
+  $NCU --set full --import-source on -k regex:$k -c 2 -o $out/prof_${k}_$tag -f python tools/observe_probe.py > $out/full_${k}_$tag.log 2>&1
+done
 python tools/ttt_probe.py > $out/ttt_probe_$tag.log 2>&1 && \
 $NCU --set full --import-source on -k regex:ttt_step -s 40 -c 1 -o $out/prof_ttt_step_$tag -f python tools/ttt_probe.py > $out/full_ttt_step_$tag.log 2>&1
 ls -la $out/*_$tag* | awk '{print $5, $9}'

@@ -86,12 +86,12 @@ def graph_dram(tag):
             json.dump({"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "launches": steps,
                        "note": "dram__bytes_read.sum + dram__bytes_write.sum of the whole timed graph / its steps "
                                "(ncu --graph-profiling graph --cache-control none: launches back to back, write-backs included)",
-                       "source": "profiles/%s_graph_dram.md" % tag},
+                       "source": "profiles/r02_graph_dram.md"},
                       open(os.path.join(PROF, "traffic_%s.json" % w), "w"), indent=1)
     lines += ["", "`dram__throughput` is relative to ncu's nominal peak (8 TB/s); bench.py's roofline uses the measured copy",
               "bandwidth (MEASURED_PEAKS.json, 6 551 GB/s).  tron_s4 = four parallel chains (the bench default), tron_s1 = one",
               "dependent chain."]
-    open(os.path.join(PROF, "%s_graph_dram.md" % tag), "w").write("\n".join(lines) + "\n")
+    open(os.path.join(PROF, "r02_graph_dram.md"), "w").write("\n".join(lines) + "\n")
 
 
 def main():
@@ -99,14 +99,14 @@ def main():
     for w in ("tron", "blokus", "ttt4"):
         src = os.path.join(OUT, "launches_%s_%s.csv" % (w, tag))
         if os.path.exists(src):
-            ncu_summary.launches(src, os.path.join(PROF, "%s_launches_%s.md" % (tag, w)))
+            ncu_summary.launches(src, os.path.join(PROF, "r02_launches_%s.md" % w))
     if os.path.exists(os.path.join(OUT, "launches_blokus_%s.csv" % tag)):
         print(json.dumps(blokus_inst(tag))[:400])
     graph_dram(tag)
-    for k in ("tron_step", "ttt_rollout", "ttt_step", "blokus_legal", "blokus_step", "observe"):
+    for k in ("tron_step", "ttt_rollout", "ttt_step", "blokus_legal", "blokus_step", "tron_observe", "blokus_observe", "ttt_observe"):
         src = os.path.join(OUT, "prof_%s_%s.ncu-rep" % (k, tag))
         if os.path.exists(src):
-            ncu_summary.full(src, os.path.join(PROF, "%s_%s_full.md" % (tag, k)))
+            ncu_summary.full(src, os.path.join(PROF, "r02_%s_full.md" % k))
 
 
 if __name__ == "__main__":
