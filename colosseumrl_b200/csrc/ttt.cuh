@@ -360,11 +360,22 @@ __device__ __forceinline__ uint32_t ttt_fused_result(const TTTFusedOut &o) {
 
 // episode statistics of a fused step into the packed counters of TTTStatAcc; the reward bias the flush removes is
 // added once per flush (TTTStatAcc::bias_from_steps)
+// acc += v if cond (0 / 1): a predicated add (FMA pipe) instead of SEL + add (the compiler's choice for `c ? v : 0`)
+__device__ __forceinline__ void ttt_add_if(uint32_t &acc, uint32_t cond, uint32_t v) {
+#ifndef CRL_HOSTSIM
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p add.u32 %0, %0, %2;\n\t}" : "+r"(acc) : "r"(cond), "r"(v));
+#else
+    if (cond) acc += v;
+#endif
+}
 __device__ __forceinline__ void ttt_fused_stats(TTTStatAcc &acc, const TTTFusedOut &o) {
-    acc.A += 1u + (o.terminal ? (o.win ? 0x100u : 0x10100u) : 0u);           // steps | episodes << 8 | episodes without a winner << 16
-    acc.W += ((o.win << o.mover) * 0x00204081u) & 0x01010101u;              // bit q -> byte q
-    acc.D += o.n + (o.terminal ? (o.ep_top >> 27) << 12 : 0u);
-    acc.R += o.win ? o.mover + 1u : 0u;
+    acc.A += 1u;                                                            // steps
+    ttt_add_if(acc.A, o.terminal, 0x10100u);                                // episodes << 8 | episodes without a winner << 16
+    ttt_add_if(acc.A, o.win, 0u - 0x10000u);                                // ... a win is not one of those (win => terminal)
+    ttt_add_if(acc.W, o.win, 1u << (8u * o.mover));                         // wins per seat, one byte each
+    acc.D += o.n;                                                           // valid-action count
+    ttt_add_if(acc.D, o.terminal, o.ep_top >> 15);                          // episode length << 12 (ep_top has bits 27..31 only)
+    ttt_add_if(acc.R, o.win, o.mover + 1u);                                 // (mover + 1) * reward
 }
 
 // K fused random-policy steps with auto-reset; grid-stride like the step kernel (a thread owns <= TTT_ACC_MAX
