@@ -755,6 +755,23 @@ def measure_b200(name, args, cx, with_cpu):
     (e2e_ms,) = cx.max_over_ranks([e0.elapsed_time(e1)])
     e2e_value = world * B * Ke / (e2e_ms * 1e-3)
     clk = clocks.stop()
+    # the same leg through the copy engines (memcpy H2D + kernel + memcpy D2H per step) next to the zero-copy transport
+    e2e_copy = None
+    if getattr(work, "stepper_kwargs", {}).get("zero_copy") and not args.no_e2e:
+        work.steppers, work.inflight = None, []
+        work.stepper_kwargs = dict(work.stepper_kwargs, zero_copy=False)
+        work.e2e_run(k, 48); k += 48
+        n_c = max(K, Ke // 3)
+        torch.cuda.synchronize()
+        cx.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        work.e2e_run(k, n_c); k += n_c
+        c1.record(stream)
+        torch.cuda.synchronize()
+        (c_ms,) = cx.max_over_ranks([c0.elapsed_time(c1)])
+        e2e_copy = {"value": world * B * n_c / (c_ms * 1e-3), "steps": n_c,
+                    "transport": "the same steps with explicit copies: one graph launch = memcpy H2D + step kernel + memcpy D2H"}
 
     out = None
     if rank == 0:
@@ -802,7 +819,8 @@ def measure_b200(name, args, cx, with_cpu):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": work.h2d,
                     "d2h_bytes_per_step": work.d2h, "steps": Ke,
                     "transport": getattr(work, "e2e_note", "one graph launch per step = memcpy H2D of the pinned actions + "
-                                         "step kernel + memcpy D2H of the result record into pinned memory")},
+                                         "step kernel + memcpy D2H of the result record into pinned memory"),
+                    "copy_engine": e2e_copy},
             "gpu_launches": n_timed * wl["launches"] * world + world,
             "clocks": clk,
             "wall_s_timed_region": wall,
