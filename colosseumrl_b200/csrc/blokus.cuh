@@ -57,15 +57,20 @@
 #define BLK_MAX_ANCHORS 400
 
 #define BLK_FSLOTS (BLK_NSHAPE_LE4 + BLK_GROUP_MAX)
+#define BLK_OFF_LE4 8           // bit offset of column 0 in the FIT boards of shapes of <= 4 cells
+#define BLK_OFF_PENT 12         // ... and of the pentomino shapes
 
 // per-warp shared scratch
 struct BlkSmem {
     uint32_t st[BLK_WORDS];          // the game state (old board during a step)
     uint32_t A[24];                  // allowed rows << 4 (bit x + 4); rows 20..23 are zero (shapes are at most 5 rows tall)
     uint32_t anc[20];                // anchor rows (bit x)
-    alignas(16) uint32_t F[BLK_FSLOTS * BLK_FROWS + 4];   // FIT boards: bit (x + 4) of word [slot * BLK_FROWS + y + 4];
-                                     // the zero padding (rows -4..-1, 20..24, bits 0..3) makes FIT_s[a - cell] a plain
-                                     // load + shift for every anchor a and shape cell, and a tree step branch-free
+    alignas(16) uint32_t F[BLK_FSLOTS * BLK_FROWS + 4];   // FIT boards: bit (x + BLK_OFF(n)) of word [slot * BLK_FROWS + y + 4]
+                                     // with BLK_OFF = 8 for shapes of <= 4 cells and 12 for pentominoes: a board is built
+                                     // with LEFT shifts only (IMADs on the FMA pipe -- the ALU pipe is this kernel's busy
+                                     // one), each level landing 4 bits above its inputs.  The zero padding (rows -4..-1,
+                                     // 20..24, the bits below the offset) makes FIT_s[a - cell] a plain load + shift for
+                                     // every anchor a and shape cell, and a tree step branch-free
     // anchors, row-major, 16 bits each: (4 * y) << 9 | x, then >= 4 padding entries (column 24: outside every FIT
     // board).  One PRMT expands an entry to w = (4 * y) << 25 | x: the low 5 bits feed a wrap-mode funnel shift
     // directly, the top 7 are the byte offset of FIT row y.
@@ -144,7 +149,7 @@ __device__ __forceinline__ void blk_zero_fit(BlkSmem &sm, int lane) {
 
 // shape 0 (the monomino): FIT = A.  Returns its non-empty flag.
 __device__ __forceinline__ uint32_t blk_tree_root(BlkSmem &sm, int lane) {
-    const uint32_t f = lane < 20 ? sm.A[lane] : 0u;
+    const uint32_t f = lane < 20 ? sm.A[lane] << (BLK_OFF_LE4 - 4) : 0u;
     if (lane < 20) sm.F[4 + lane] = f;
     const uint32_t ne = __any_sync(0xffffffffu, f != 0u) ? 1u : 0u;
     __syncwarp();
@@ -162,11 +167,12 @@ __device__ __forceinline__ uint32_t blk_tree_pass(BlkSmem &sm, int s0, int s1, u
         const char *pp = (const char *)sm.F + (t.x & 0xffffu);      // parent row 4 + py
         const char *pa = (const char *)sm.A + (t.x >> 24);          // A row cy
         char *po = (char *)sm.F + (t.w & 0xffffu);                  // own row 4
-        const uint32_t px = t.x >> 16, cx = t.x >> 20;              // wrap-mode shifts use the low 5 bits: px, cx <= 4
+        // parent bit (qx + px + 8) and A bit (qx + cx + 4) both land on qx + 12: two multiplies by powers of two.  No
+        // mask is needed: the shape has a cell in column 0, so px == 0 or cx == 0 and that term has no bit below 12.
+        const uint32_t mp = 1u << (BLK_OFF_PENT - BLK_OFF_LE4 - ((t.x >> 16) & 7u)), mc = 1u << (BLK_OFF_PENT - 4 - ((t.x >> 20) & 7u));
 #pragma unroll 10
         for (int r = 0; r < 20; r++) {
-            const uint32_t f = __funnelshift_r(*(const uint32_t *)(pp + 4 * r), 0u, px & 7u) &
-                               __funnelshift_r(*(const uint32_t *)(pa + 4 * r), 0u, cx & 7u) & 0xfffffff0u;
+            const uint32_t f = (*(const uint32_t *)(pp + 4 * r) * mp) & (*(const uint32_t *)(pa + 4 * r) * mc);
             *(uint32_t *)(po + 4 * r) = f;
             acc |= f;
         }
@@ -188,12 +194,14 @@ __device__ __forceinline__ uint32_t blk_tree_pass_le4(BlkSmem &sm, uint32_t ne, 
     if (active) {
         const char *a0 = (const char *)sm.A + 4 * (t.z >> 3 & 7u), *a1 = (const char *)sm.A + 4 * (t.z >> 9 & 7u);
         const char *a2 = (const char *)sm.A + 4 * (t.z >> 15 & 7u), *a3 = (const char *)sm.A + 4 * (t.z >> 21 & 7u);
-        const uint32_t x0 = t.z & 7u, x1 = t.z >> 6 & 7u, x2 = t.z >> 12 & 7u, x3 = t.z >> 18 & 7u;
+        // A bit (qx + dx_i + 4) lands on qx + 8: a multiply by 2^(4 - dx_i) per cell (IMAD; a right shift is an ALU-pipe SHF).
+        // No mask: the cell in column 0 contributes no bit below 8.
+        const uint32_t m0 = 16u >> (t.z & 7u), m1 = 16u >> (t.z >> 6 & 7u), m2 = 16u >> (t.z >> 12 & 7u), m3 = 16u >> (t.z >> 18 & 7u);
         char *po = (char *)sm.F + (t.w & 0xffffu);                  // own row 4
 #pragma unroll 10
         for (int r = 0; r < 20; r++) {
-            const uint32_t f = (*(const uint32_t *)(a0 + 4 * r) >> x0) & (*(const uint32_t *)(a1 + 4 * r) >> x1) &
-                               (*(const uint32_t *)(a2 + 4 * r) >> x2) & (*(const uint32_t *)(a3 + 4 * r) >> x3) & 0xfffffff0u;
+            const uint32_t f = (*(const uint32_t *)(a0 + 4 * r) * m0) & (*(const uint32_t *)(a1 + 4 * r) * m1) &
+                               (*(const uint32_t *)(a2 + 4 * r) * m2) & (*(const uint32_t *)(a3 + 4 * r) * m3);
             *(uint32_t *)(po + 4 * r) = f;
             acc |= f;
         }
@@ -222,8 +230,9 @@ __device__ __forceinline__ bool blk_any_pass(BlkSmem &sm, int s0, int s1, int n,
         // OR_k shift(FIT_s, cell_k) & ANC on the anchor rows (short shapes repeat cell 0)
         const char *p0 = po - 4 * (int)(t.z >> 3 & 7u), *p1 = po - 4 * (int)(t.z >> 9 & 7u), *p2 = po - 4 * (int)(t.z >> 15 & 7u);
         const char *p3 = po - 4 * (int)(t.z >> 21 & 7u), *p4 = po - 4 * (int)(t.z >> 27 & 7u);
-        const uint32_t h0 = 4u - (t.z & 7u), h1 = 4u - (t.z >> 6 & 7u), h2 = 4u - (t.z >> 12 & 7u);
-        const uint32_t h3 = 4u - (t.z >> 18 & 7u), h4 = 4u - (t.z >> 24 & 7u);
+        const uint32_t off = n > 4 ? BLK_OFF_PENT : BLK_OFF_LE4;     // column 0 of these boards
+        const uint32_t h0 = off - (t.z & 7u), h1 = off - (t.z >> 6 & 7u), h2 = off - (t.z >> 12 & 7u);
+        const uint32_t h3 = off - (t.z >> 18 & 7u), h4 = off - (t.z >> 24 & 7u);
 #pragma unroll 1
         for (uint32_t rm = rows; rm; rm &= rm - 1u) {
             const int r4 = 4 * (__ffs((int)rm) - 1);

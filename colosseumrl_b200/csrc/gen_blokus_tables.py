@@ -204,7 +204,8 @@ def emit(path):
 
     L.append("// per (piece, orientation), read by the lanes that own the orientation during emission, 12 x uint16, every field")
     L.append("// directly usable (no unpacking):  [0..4] byte offset of FIT row (4 - dy_k) of the orientation's slot for shift")
-    L.append("// k = 0..4 (the shape cell (dx_k, dy_k) sits on the anchor; id = o * 5 + k), [5..9] 4 - dx_k, [10] non-empty flag")
+    L.append("// k = 0..4 (the shape cell (dx_k, dy_k) sits on the anchor; id = o * 5 + k), [5..9] OFF - dx_k (OFF = 8 for pieces of")
+    L.append("// <= 4 cells, 12 for pentominoes: the column-0 bit of their FIT boards), [10] non-empty flag")
     L.append("// index (s for <= 4 cells: bit of `ne`; s - group start for pentominoes: bit of the group's `ne5`), [11] unused")
     L.append("// (32-bit entries, three 128-bit loads per lane and piece: 16-bit entries cost eleven LDG.U16)")
     L.append("__device__ const uint4 BLK_ORIENT_TAB_G[BLK_NPIECE * 8][3] = {")
@@ -212,7 +213,7 @@ def emit(path):
         slot, flag = slot_flag(s_)
         cl = list(cells) + [cells[0]] * (5 - len(cells))
         offs = [(slot * FROWS + 4 - dy) * 4 for dx, dy in cl]
-        cs = [4 - dx for dx, dy in cl]
+        cs = [(12 if len(cells) == 5 else 8) - dx for dx, dy in cl]    # BLK_OFF_PENT / BLK_OFF_LE4 of blokus.cuh
         v = offs + cs + [flag, 0]
         L.append("    {" + ", ".join("{%d, %d, %d, %d}" % tuple(v[4 * j:4 * j + 4]) for j in range(3)) + "},")
     L.append("};")
