@@ -630,6 +630,7 @@ blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, in
                       uint8_t *__restrict__ pieces, int32_t *__restrict__ score, int32_t *__restrict__ meta) {
     __shared__ uint32_t sst[BLK_OBS_WARPS][BLK_WORDS];
     __shared__ __align__(16) uint32_t stage[BLK_OBS_WARPS][100];
+    __shared__ __align__(16) uint32_t pstage[BLK_OBS_WARPS][24];         // the game's 84 inventory bytes (+ padding)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long g = (long long)blockIdx.x * BLK_OBS_WARPS + wid;
     if (g >= B) return;
@@ -659,15 +660,16 @@ blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, in
     //    player 0 / absolute: (y, x)    1: (x, 19 - y)    2: (19 - y, 19 - x)    3: (19 - x, y)
     //    i.e. at byte  base + stride * x  of the staging tile, with base and stride constants of the lane
     if (lane < 20) {
-        const uint32_t emp = rel ? 255u : 0u;
+        // three nibble -> bytes spreads per 4 cells, not four: a relative view has labels 0..3 (no bit 2) and -1 for the
+        // empty cells; the absolute view has labels 1..4 and 0 for the empty cells (no empty plane)
+        const uint32_t xt = rel ? xe : x2, kt = rel ? 255u : 4u;
         uint32_t w[5];
 #pragma unroll
         for (int q = 0; q < 5; q++) {
             const uint32_t b0 = (((x0 >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
             const uint32_t b1 = (((x1 >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
-            const uint32_t b2 = (((x2 >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
-            const uint32_t be = (((xe >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
-            w[q] = b0 + 2u * b1 + 4u * b2 + emp * be;
+            const uint32_t bt = (((xt >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
+            w[q] = b0 + 2u * b1 + kt * bt;
         }
         if (player <= 0) {
             uint32_t *o = stage[wid] + 5 * lane;
@@ -685,11 +687,19 @@ blokus_observe_kernel(const uint4 *__restrict__ st4, long long B, int player, in
     }
     __syncwarp();
     if (lane < 25) ((uint4 *)(board + g * 400))[lane] = ((const uint4 *)stage[wid])[lane];
-    for (int idx = lane; idx < 84; idx += 32) {             // pieces[rel][piece]
-        const int r = idx / 21, p = idx - r * 21;
-        const int src = player >= 0 ? ((r + player) & 3) : r;
-        pieces[g * 84 + idx] = (uint8_t)(s[80 + src] >> p & 1u);
+    // pieces[rel][piece]: lane p < 21 owns piece p of the four rows (4 byte stores into the staging tile), then the 84
+    // bytes leave as 21 words (a game's inventory block starts at g * 84: 4-byte aligned).  (Three passes of 32 bytes with
+    // a division each cost 90 of the kernel's 410 warp instructions per game.)
+    if (lane < BLK_NPIECE) {
+        uint8_t *pb = (uint8_t *)pstage[wid] + lane;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int src = player >= 0 ? ((r + player) & 3) : r;
+            pb[21 * r] = (uint8_t)(s[80 + src] >> lane & 1u);
+        }
     }
+    __syncwarp();
+    if (lane < 21) ((uint32_t *)(pieces + g * 84))[lane] = pstage[wid][lane];
     if (lane < 4) {
         const int src = player >= 0 ? ((lane + player) & 3) : lane;
         score[g * 4 + lane] = (int)(s[84] >> (8 * src) & 0xffu);
