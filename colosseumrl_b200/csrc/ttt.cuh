@@ -486,7 +486,8 @@ ttt_observe_kernel(const uint4 *__restrict__ st, long long B, int player, int8_t
     for (int j = 0; j < NP; j++) {                           // word j = player (mover + j) % NP
         int p = s.mover + j;
         p -= p >= NP ? NP : 0;
-        const int code = viewer < 0 ? p : ((p - viewer) % MOD + MOD) % MOD;
+        // ((p - viewer) mod MOD) for p - viewer in -3..3 from a 2-bit-per-entry constant (no integer modulo per lane)
+        const int code = viewer < 0 ? p : (int)(((MOD == 3 ? 0x924u : 0x110u) >> (2 * (p - viewer + 3))) & 3u);
         b0 |= (code & 1) ? s.c[j] : 0u;
         b1 |= (code & 2) ? s.c[j] : 0u;
     }
