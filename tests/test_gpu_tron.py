@@ -66,6 +66,8 @@ def test_wide_rollout_vs_oracle(be):
     cases.case_rollout_vs_oracle(be, N=21, P=4, B=300, K=60, seed=4)
     cases.case_rollout_vs_oracle(be, N=11, P=6, B=500, K=40, seed=5)
     cases.case_rollout_vs_oracle(be, N=25, P=8, B=2000, K=50, seed=6, env0=77)
+    cases.case_rollout_vs_oracle(be, N=64, P=8, B=70, K=90, seed=7)            # the largest shape: 128 words per plane
+    cases.case_rollout_vs_oracle(be, N=20, P=2, B=129, K=120, seed=8)          # the smallest wide shape
 
 
 def test_wide_adversarial(be):

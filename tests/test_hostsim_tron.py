@@ -56,6 +56,7 @@ def test_start_positions_golden(be):
 def test_wide_rollout_vs_oracle(be):
     cases.case_rollout_vs_oracle(be, N=21, P=4, B=40, K=40, seed=4)
     cases.case_rollout_vs_oracle(be, N=11, P=6, B=70, K=30, seed=5)
+    cases.case_rollout_vs_oracle(be, N=64, P=8, B=8, K=40, seed=7)             # the largest shape: 128 words per plane
 
 
 def test_wide_adversarial(be):
