@@ -28,7 +28,18 @@ from .tictactoe import BatchedTicTacToe2PlayerEnv, BatchedTicTacToe3PlayerEnv, B
 from .tron import BatchedTronGridEnvironment
 
 
-class SingleEnvironment:
+def _reference_base():
+    """The reference's own ABC (colosseumrl/BaseEnvironment.py:10) when that package is importable -- the adapters are
+    then real `BaseEnvironment` subclasses, as `server_app` / `RllibWrapper` type-annotate them -- else `object` (the
+    engine does not depend on the reference being installed)."""
+    try:
+        from colosseumrl.BaseEnvironment import BaseEnvironment
+        return BaseEnvironment
+    except Exception:
+        return object
+
+
+class SingleEnvironment(_reference_base()):
     """Common part of the adapters (BaseEnvironment.py:10-283)."""
     _batched_class = None
 

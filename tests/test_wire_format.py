@@ -90,3 +90,25 @@ def test_untouched_reference_consumes_our_stream():
     for i in range(20):
         state, players, _, _, _ = env.next_state(state, players, [orc.blokus_action_to_string(int(g["action"][i]))])
     _same_state(BlokusEnvironment.deserialize_state(env.serialize_state(state)), expect)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.available(), reason="needs /root/reference (build container only)")
+def test_adapters_subclass_the_reference_abc_when_it_is_importable():
+    """With the reference package importable, the single-environment adapters ARE `BaseEnvironment` subclasses with no
+    abstract member left open (colosseumrl/BaseEnvironment.py:10-283); without it they fall back to plain classes."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from oracle import ref_shim; ref_shim.load()\n"
+            "from colosseumrl.BaseEnvironment import BaseEnvironment\n"
+            "import colosseumrl_b200.single as s\n"
+            "for c in s.ENVIRONMENT_CLASSES.values():\n"
+            "    assert issubclass(c, BaseEnvironment), c\n"
+            "    assert not getattr(c, '__abstractmethods__', None), (c, c.__abstractmethods__)\n"
+            "print('ok', len(s.ENVIRONMENT_CLASSES))\n" % root)
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "ok 5", out.stderr[-1500:]
+    from colosseumrl_b200 import single
+    assert single.SingleEnvironment.__mro__[1] is object or single.SingleEnvironment.__mro__[1].__name__ == "BaseEnvironment"
