@@ -565,15 +565,14 @@ class Ctx:
         return [float(x) for x in t.tolist()]
 
 
-def issue_roofline(args, stats, launch_ms_step, clk):
+def issue_roofline(args, stats, launch_ms_step, clk, B):
     """Blokus against the integer ISSUE roof: warp instructions per env-step (committed ncu count of this very
     workload, profiles/blokus_inst.json) x env-steps/s  vs  4 warp-instructions / clk / SM (INT_PEAKS.json)."""
     inst = _load_json("profiles", "blokus_inst.json")
     ip = _load_json("INT_PEAKS.json")
     if not inst or not ip or not inst.get("warp_inst_per_env_step"):
         return None
-    B = WORKLOADS["blokus"]["B"]
-    per_step = float(inst["warp_inst_per_env_step"])
+    per_step = float(inst["warp_inst_per_env_step"])         # (B = games per launch on this rank: the per-GPU batch)
     achieved = per_step * B / (launch_ms_step * 1e-3) / 1e12
     mhz = float((clk or {}).get("sm_mhz") or ip.get("sm_mhz", 1965.0))
     peak = 4.0 * ip.get("sms", 148) * mhz * 1e6 / 1e12
@@ -795,7 +794,7 @@ def measure_b200(name, args, cx, with_cpu):
             next_state_only["frac"] = 41 * B / (next_state_only["ms_per_step"] * 1e-3) / 1e9 / peak
             hbm["next_state_only"] = next_state_only
         if name == "blokus":
-            issue = issue_roofline(args, stats, step_ms, clk)
+            issue = issue_roofline(args, stats, step_ms, clk, B)
             if issue is not None:
                 issue.update(kernel=wl["kernel"], launch_ms=launch_ms, traffic=traffic, hbm=hbm,
                              note="integer issue binds this path (SURVEY 8d); the HBM figure is kept as `hbm`")
