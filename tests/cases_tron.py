@@ -182,10 +182,12 @@ def case_golden_steps(be, path):
     assert (be.download(ade).reshape(n * P, P) == g["obs_deaths"]).all()
 
 
-def case_adversarial(be):
-    g = np.load(os.path.join(GOLDEN, "tron_adversarial.npz"))
-    for N in (5, 6, 7):
-        for P in (2, 3, 4):
+def case_adversarial(be, name="tron_adversarial.npz"):
+    """Hand-built states stepped by the REFERENCE (tests/golden/tron_adversarial.npz; `tron_adversarial_wide.npz`,
+    oracle/make_golden_tron_wide.py: 5..8 players and / or boards beyond 19x19 -- the wide path)."""
+    g = np.load(os.path.join(GOLDEN, name))
+    for N in sorted(set(g["N"].tolist())):
+        for P in sorted(set(g["P"].tolist())):
             m = (g["N"] == N) & (g["P"] == P)
             if not m.any():
                 continue

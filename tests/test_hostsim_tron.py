@@ -28,6 +28,10 @@ def test_adversarial(be):
     cases.case_adversarial(be)
 
 
+def test_adversarial_wide_reference_recorded(be):
+    cases.case_adversarial(be, "tron_adversarial_wide.npz")
+
+
 def test_rollout_vs_oracle(be):
     cases.case_rollout_vs_oracle(be, N=19, P=4, B=130, K=30)
     cases.case_rollout_vs_oracle(be, N=7, P=3, B=40, K=30, seed=9)
