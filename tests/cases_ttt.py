@@ -121,3 +121,31 @@ def case_masked_reset_and_errors(be):
     r = unpack_result(be.download(res))
     board, winner, mover = ttt_unpack(be, out, 2)
     assert r["error"].all() and not r["placed"].any() and (board == -1).all() and (mover == 1).all()
+
+
+def case_arbitrary_states(be, n):
+    """tests/golden/ttt_states.npz (oracle/make_golden_ttt_states.py): arbitrary states stepped by the REFERENCE --
+    carried winners that contradict the board, full boards, occupied-cell actions -- valid masks, next_state outputs
+    and one observation each."""
+    g = np.load(os.path.join(GOLDEN, "ttt_states.npz"))
+    k = lambda name: g["p%d_%s" % (n, name)]
+    T, cells = len(k("mover")), orc.ttt_cells(n)
+    st = ttt_pack(be, n, k("board"), k("winner"), k("mover"))
+    vm = be.zeros((T,), np.uint32)
+    be.check(be.lib.crl_ttt_valid_actions(be.ptr(st), be.ptr(vm), T, n, be.stream))
+    vmask = be.download(vm).view(np.uint32)
+    assert (np.array([bin(int(m)).count("1") for m in vmask]) == k("n_valid")).all()
+    assert (vmask == ((k("board") == -1).astype(np.uint64) << np.arange(cells, dtype=np.uint64)[None]).sum(1)).all()
+    act = be.upload(k("action").astype(np.int8))
+    res, out = be.zeros((T, 4), np.uint8), be.zeros((T, 4), np.int32)
+    be.check(be.lib.crl_ttt_step(be.ptr(st), be.ptr(out), be.ptr(act), be.ptr(res), None, None, T, n, 0, be.stream))
+    r = unpack_result(be.download(res))
+    board, winner, mover = ttt_unpack(be, out, n)
+    assert (board == k("o_board")).all() and (winner == k("o_winner")).all() and (mover == k("next_player")).all()
+    assert (r["reward"] == k("reward")).all() and (r["terminal"] == k("terminal").astype(bool)).all()
+    assert (r["winners"] == np.where(k("winners") >= 0, 1 << np.maximum(k("winners"), 0), 0)).all()
+    for p in range(n):
+        sel = np.flatnonzero(k("viewer") == p)
+        sub = ttt_pack(be, n, k("o_board")[sel], k("o_winner")[sel], k("next_player")[sel])
+        ob, _, _ = ttt_unpack(be, sub, n, player=p)
+        assert (ob == k("obs")[sel]).all(), p

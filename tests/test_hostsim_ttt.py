@@ -26,3 +26,8 @@ def test_rollout_vs_oracle(be, n):
 
 def test_masked_reset_and_errors(be):
     cases.case_masked_reset_and_errors(be)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_arbitrary_states_reference_recorded(be, n):
+    cases.case_arbitrary_states(be, n)
