@@ -145,6 +145,25 @@ def case_wide_golden(be, stride=1):
     _check_wide(be, e, "e_", e["e_i_board"], e["e_i_inventory"], e["e_i_scores"], e["e_i_round"])
 
 
+def case_arbitrary_positions(be):
+    """tests/golden/blokus_boards.npz (oracle/make_golden_blokus_boards.py): arbitrary hand-built positions stepped by the
+    REFERENCE -- every seat's ordered valid list (length + order-sensitive hash) and one next_state of the mover."""
+    g = np.load(os.path.join(GOLDEN, "blokus_boards.npz"))
+    n = len(g["mover"])
+    for q in range(4):
+        st = blk_pack(be, g["i_board"], g["i_inventory"], g["i_scores"], g["i_round"], np.full(n, (q + 1) % 4))
+        counts, ids = blk_legal(be, st, player=q, cap=4096)
+        assert (counts == g["n_valid"][:, q]).all(), q
+        assert (_list_hashes(counts, ids) == g["valid_hash"][:, q]).all(), q
+    st = blk_pack(be, g["i_board"], g["i_inventory"], g["i_scores"], g["i_round"], g["mover"])
+    out, r = blk_step(be, st, g["action"])
+    b2, p2, s2, m2 = blk_unpack(be, out)
+    assert (b2 == g["board"]).all() and (p2 == g["inventory"]).all() and (s2 == g["scores"]).all()
+    assert (m2[:, 0] == g["round"]).all() and (m2[:, 1] == g["next_mover"]).all() and (m2[:, 2] == g["terminal"]).all()
+    assert (r["reward"] == g["reward"]).all() and (r["terminal"] == g["terminal"]).all() and (r["winners"] == g["winners"]).all()
+    assert not r["error"].any()
+
+
 def case_illegal_actions(be):
     """Ids outside the mover's valid list are flagged and applied as a pass (engine contract)."""
     g = np.load(os.path.join(GOLDEN, "blokus_games.npz"))

@@ -53,3 +53,7 @@ def test_is_valid(be):
 
 def test_wide_golden(be):
     cases.case_wide_golden(be)
+
+
+def test_arbitrary_positions_reference_recorded(be):
+    cases.case_arbitrary_positions(be)

@@ -40,3 +40,7 @@ def test_is_valid(be):
 
 def test_wide_golden(be):
     cases.case_wide_golden(be, stride=9)
+
+
+def test_arbitrary_positions_reference_recorded(be):
+    cases.case_arbitrary_positions(be)
