@@ -455,60 +455,41 @@ class BlokusWL:
         env.step_(st, self.act[g], out=st)                            # crl_blokus_step
         self.local_t[g] += 1
 
-    # e2e: a host-side policy needs two round trips per step -- it sees the list lengths (D2H), picks an index into
-    # the device-side list (H2D of one int32 per game; here: entry 0, -1 = pass), the step runs, the result record
-    # comes back (D2H).  The actor pipelines its G independent batches, one stream each: while batch g waits for its
-    # counts, batches g-1 .. g-4 are stepping and g-5 .. g-8 are delivering results.
+    # e2e: a host-side policy needs two round trips per step -- it sees the list lengths (D2H), answers with an index
+    # into the device-side list (H2D of one int32 per game; here: entry 0, pass if the list is empty), the step runs, the
+    # result record comes back (D2H).  Public API: env.host_stepper(state) -> BlokusHostStepper, two graph launches per
+    # step.  The actor pipelines its G independent batches, one stream each: while batch g waits for its counts,
+    # batches g-1 .. g-4 are stepping and g-5 .. g-8 are delivering results.
     E2E_LAG = 4
 
     def _e2e_init(self):
         torch = self.torch
         dev = self.envs[0].device
         self.es = [torch.cuda.Stream(dev) for _ in range(self.G)]
-        self.ev_a = [torch.cuda.Event() for _ in range(self.G)]
-        self.ev_b = [torch.cuda.Event() for _ in range(self.G)]
-        self.hc = [torch.empty((self.B,), dtype=torch.int32).pin_memory() for _ in range(self.G)]
-        self.hr = [torch.empty((self.B, 8), dtype=torch.uint8).pin_memory() for _ in range(self.G)]
+        self.sps = [e.host_stepper(s, stream=self.es[g]) for g, (e, s) in enumerate(zip(self.envs, self.states))]
         self.qa, self.qb = [], []
+        for sp in self.sps:                                # untimed warm-up of every batch's two graphs
+            sp.choice_np[:] = 0                            # the host policy's answer: the first entry of the list
+            sp.legal()
+            sp.step()
         torch.cuda.synchronize(dev)
-        # untimed warm-up of EVERY batch's pipeline: the first use of a stream makes the caching allocator cudaMalloc a
-        # pool for it (milliseconds, device-synchronising) -- that belongs to start-up, not to a steady-state step
-        for g in range(self.G):
-            with torch.cuda.stream(self.es[g]):
-                counts, _ = self.envs[g].valid_actions(self.states[g], -1, out=self.valid[g])
-                self.hc[g].copy_(counts, non_blocking=True)
-                self.ev_a[g].record()
-            self._e2e_phase_b(g)
-            self._e2e_phase_c(self.qb.pop(0))
-        torch.cuda.synchronize(dev)
+        self.e2e_note = ("env.host_stepper(state): two graph launches per step -- crl_blokus_legal + D2H of the list lengths; "
+                         "H2D of the policy's index + crl_blokus_pick + crl_blokus_step + D2H of the result records")
 
     def _e2e_phase_b(self, g):
-        torch = self.torch
-        env, st = self.envs[g], self.states[g]
-        self.ev_a[g].synchronize()
-        _ = int(self.hc[g][0])                                        # the host policy reads the list lengths
-        counts, ids = self.valid[g]
-        with torch.cuda.stream(self.es[g]):
-            idx = self.h_actions.to(env.device, non_blocking=True)    # H2D: the host's choice (-1 -> entry 0)
-            act = torch.where(counts > 0, ids[:, 0], idx)
-            new = env.step_(st, act, out=st)
-            self.hr[g].copy_(new.result, non_blocking=True)
-            self.ev_b[g].record()
+        sp = self.sps[g]
+        _ = int(sp.wait_legal()[0])                        # the host policy reads the list lengths
+        sp.launch_step()
         self.qb.append(g)
 
     def _e2e_phase_c(self, g):
-        self.ev_b[g].synchronize()
-        return int(self.hr[g][0, 1])                                  # the host reads the result record
+        return int(self.sps[g].wait_step()[0, 1])          # the host reads the result record
 
     def e2e_step(self, k):
-        torch = self.torch
         if getattr(self, "es", None) is None:
             self._e2e_init()
         g = k % self.G
-        with torch.cuda.stream(self.es[g]):
-            counts, _ = self.envs[g].valid_actions(self.states[g], -1, out=self.valid[g])
-            self.hc[g].copy_(counts, non_blocking=True)
-            self.ev_a[g].record()
+        self.sps[g].launch_legal()
         self.qa.append(g)
         if len(self.qa) > self.E2E_LAG:
             self._e2e_phase_b(self.qa.pop(0))

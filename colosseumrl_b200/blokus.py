@@ -6,6 +6,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .base import BatchedBaseEnvironment
+from . import _lib
 
 PIECE_NAMES = ["monomino1", "domino1", "trominoe1", "trominoe2", "tetrominoes1", "tetrominoes2", "tetrominoes3",
                "tetrominoes4", "tetrominoes5"] + ["pentominoe%d" % i for i in range(1, 13)]   # board.py:24-44
@@ -160,6 +161,10 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
                                               self._stream))
         return new
 
+    def host_stepper(self, state: BlokusBatchState, stream=None) -> "BlokusHostStepper":
+        """Two graph launches per game step for a policy that runs on the host (see BlokusHostStepper)."""
+        return BlokusHostStepper(self, state, stream=stream)
+
     def is_terminal(self, state: BlokusBatchState) -> torch.Tensor:
         return ((state.packed[:, 21, 1] >> 16) & 1).to(torch.uint8)
 
@@ -200,3 +205,101 @@ class BatchedBlokusEnvironment(BatchedBaseEnvironment):
         self._check(self._lib.crl_blokus_policy_random(counts.data_ptr(), ids.data_ptr(), ids.shape[1], out.data_ptr(),
                                                        self.seed, self.first_env_id, int(step), self.batch, self._stream))
         return out
+
+
+class BlokusHostStepper:
+    """A Blokus batch driven by a policy that runs on the HOST, in two CUDA-graph launches per game step:
+
+      A  `launch_legal()`:  crl_blokus_legal (the movers' ordered valid lists stay on the device) -> D2H of the list
+                            LENGTHS into `counts_np` (pinned int32 [B])
+      B  `launch_step()`:   H2D of `choice_np` (pinned int32 [B]: index into each game's valid list, negative = pass)
+                            -> crl_blokus_pick -> crl_blokus_step (in place on `state`) -> D2H of the result records
+                            into `result_np` (pinned uint8 [B, 8])
+
+        stepper = env.host_stepper(state)
+        counts = stepper.legal()                     # launch A + wait
+        stepper.choice_np[...] = my_policy(counts)   # e.g. a random index < counts
+        records = stepper.step()                     # launch B + wait
+    The kilobytes of action ids per game never cross PCIe; an actor serving several batches pipelines them
+    (`launch_legal` / `wait_legal` / `launch_step` / `wait_step`), one stream per stepper.  `ids_device` is the
+    device-side list for policies that want to look at the ids themselves."""
+
+    def __init__(self, env, state, stream=None):
+        from . import _cudart
+        self.env, self.state = env, state
+        B, dev = env.batch, env.device
+        with torch.cuda.device(dev):
+            s = stream if stream is not None else torch.cuda.current_stream(dev)
+            self.counts = torch.zeros((B,), dtype=torch.int32).pin_memory()
+            self.choice = torch.zeros((B,), dtype=torch.int32).pin_memory()
+            self.result = torch.zeros((B, 8), dtype=torch.uint8).pin_memory()
+            self.counts_np, self.choice_np, self.result_np = self.counts.numpy(), self.choice.numpy(), self.result.numpy()
+            self._counts_dev = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self.ids_device = torch.zeros((B, env.capacity), dtype=torch.int32, device=dev)
+            self._choice_dev = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self._action_dev = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self._result_dev = torch.zeros((B, 8), dtype=torch.uint8, device=dev)
+
+            def phase_a():
+                env.valid_actions(state, -1, out=(self._counts_dev, self.ids_device))
+                self.counts.copy_(self._counts_dev, non_blocking=True)
+
+            def phase_b():
+                self._choice_dev.copy_(self.choice, non_blocking=True)
+                env._check(env._lib.crl_blokus_pick(self._counts_dev.data_ptr(), self.ids_device.data_ptr(), env.capacity,
+                                                    self._choice_dev.data_ptr(), self._action_dev.data_ptr(), B, env._stream))
+                env._check(env._lib.crl_blokus_step(state.packed.data_ptr(), state.packed.data_ptr(), self._action_dev.data_ptr(),
+                                                    self._result_dev.data_ptr(), env._stats_ptr, B, env.flags, env._stream))
+                state.result = None
+                self.result.copy_(self._result_dev, non_blocking=True)
+
+            with torch.cuda.stream(s):
+                phase_a()                                        # warm the launch paths (the state is not stepped:
+            torch.cuda.synchronize(dev)                          # phase B is only captured, never run eagerly)
+            self._graphs = []
+            for fn in (phase_a, phase_b):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                self._graphs.append(g)
+            raw = _lib.load()
+            self._launch_fn, self._wait_fn = raw.crl_host_graph_launch, raw.crl_host_event_wait
+            self._exec = [g.raw_cuda_graph_exec() for g in self._graphs]
+            self._done = [_cudart.new_event(), _cudart.new_event()]
+            self._stream_handle = s.cuda_stream
+            for e in self._exec:
+                _cudart.check(_cudart.rt().cudaGraphUpload(e, self._stream_handle), "cudaGraphUpload")
+
+    def _launch(self, i):
+        rc = self._launch_fn(self._exec[i], self._stream_handle, self._done[i])
+        if rc == _lib.ERR_ARG:                                   # wrong current device: retry under a guard
+            with torch.cuda.device(self.env.device):
+                rc = self._launch_fn(self._exec[i], self._stream_handle, self._done[i])
+        if rc:
+            raise RuntimeError("BlokusHostStepper launch failed: %s" % _lib.load().crl_last_error().decode())
+
+    def _wait(self, i):
+        if self._wait_fn(self._done[i]):
+            raise RuntimeError("BlokusHostStepper wait failed: %s" % _lib.load().crl_last_error().decode())
+
+    def launch_legal(self):
+        self._launch(0)
+
+    def wait_legal(self):
+        self._wait(0)
+        return self.counts_np
+
+    def launch_step(self):
+        self._launch(1)
+
+    def wait_step(self):
+        self._wait(1)
+        return self.result_np
+
+    def legal(self):
+        self.launch_legal()
+        return self.wait_legal()
+
+    def step(self):
+        self.launch_step()
+        return self.wait_step()

@@ -601,6 +601,17 @@ __global__ void blokus_policy_random_kernel(const int32_t *__restrict__ counts, 
     actions[g] = n > 0 ? ids[g * cap + (long long)(r.x % (uint32_t)n)] : -1;
 }
 
+// a host-side policy's choice: actions[g] = the choice[g]-th entry of game g's valid list, pass (-1) if choice[g] is
+// negative or past the end of the list.  (The policy reads the list LENGTHS on the host and answers with an index: the
+// lists themselves -- kilobytes per game -- never cross PCIe.)
+__global__ void blokus_pick_kernel(const int32_t *__restrict__ counts, const int32_t *__restrict__ ids, int cap,
+                                   const int32_t *__restrict__ choice, int32_t *__restrict__ actions, long long B) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B) return;
+    const int n = min(counts[g], cap), c = choice[g];
+    actions[g] = (c >= 0 && c < n) ? ids[g * cap + c] : -1;
+}
+
 __global__ void blokus_reset_kernel(uint4 *__restrict__ st, const uint8_t *__restrict__ mask, long long B) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * BLK_VEC) return;

@@ -759,6 +759,15 @@ int crl_blokus_policy_random(const int32_t *counts, const int32_t *action_ids, i
     return check_launch("blokus_policy_random_kernel");
 }
 
+int crl_blokus_pick(const int32_t *counts, const int32_t *action_ids, int32_t capacity, const int32_t *choice,
+                    int32_t *actions, int64_t B, crl_stream_t stream) {
+    if (!counts || !action_ids || !choice || !actions || capacity <= 0 || B < 0) return fail(CRL_ERR_ARG, "crl_blokus_pick: bad argument%s");
+    if (B == 0) return CRL_OK;
+    CRL_LAUNCH(blokus_pick_kernel, blocks_for(B, 256), 256, (cudaStream_t)stream, counts, action_ids, (int)capacity, choice,
+               actions, (long long)B);
+    return check_launch("blokus_pick_kernel");
+}
+
 int crl_blokus_observe(const void *state, int player, int8_t *board, uint8_t *pieces, int32_t *score, int32_t *meta,
                        int64_t B, crl_stream_t stream) {
     if (!state || !board || !pieces || !score || B < 0 || player > 3 || player < -2) return fail(CRL_ERR_ARG, "crl_blokus_observe: bad argument%s");

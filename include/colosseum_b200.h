@@ -228,6 +228,11 @@ int crl_blokus_step(const void *state_in, void *state_out, const int32_t *action
 /* uniform random policy over a generated list: ids[g][philox(env, step, tag 2)[0] % counts[g]], -1 if empty */
 int crl_blokus_policy_random(const int32_t *counts, const int32_t *action_ids, int32_t capacity, int32_t *actions,
                              uint64_t seed, uint64_t first_env, uint32_t step, int64_t B, crl_stream_t stream);
+/* a host-side policy's choice (the agent of match_server.py:201-218 answers with one of the strings valid_actions gave
+ * it): actions[g] = action_ids[g][choice[g]], -1 (pass) if choice[g] < 0 or >= counts[g].  The policy only needs the list
+ * lengths on the host; the lists stay on the device. */
+int crl_blokus_pick(const int32_t *counts, const int32_t *action_ids, int32_t capacity, const int32_t *choice,
+                    int32_t *actions, int64_t B, crl_stream_t stream);
 /* state_to_observation (BlokusEnvironment.py:721-768).  player >= 0: board int8[B][20][20] of relative ids (-1
  * empty) rotated by rot90(k=-player), pieces u8[B][4][21] by relative id, score int32[B][4] rolled by -player.
  * player < 0: absolute unpack (board 0 empty / 1..4 colour).  meta int32[B][4] (may be NULL) = round, mover,

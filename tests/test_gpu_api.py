@@ -296,3 +296,31 @@ def test_ttt_compact_host_stepper():
             assert (terminal == ta.cpu().numpy()).all() and (winners == wa.cpu().numpy()).all()
             terminals += int(terminal.sum()); wins += int((winners != 0).sum())
         assert terminals > 0 and wins > 0 and (sa.packed == sb.packed).all()
+
+
+def test_blokus_host_stepper():
+    """env.host_stepper (BlokusHostStepper: legal -> counts on the host -> the policy's index -> pick + step -> records)
+    plays the same games as valid_actions + next_state with the same choices; indices past the list are passes."""
+    from colosseumrl_b200.blokus import BatchedBlokusEnvironment
+    B = 96
+    a_env = BatchedBlokusEnvironment("", batch=B, seed=6, auto_reset=True)
+    b_env = BatchedBlokusEnvironment("", batch=B, seed=6, auto_reset=True)
+    sa, pa = a_env.new_state()
+    sb, _ = b_env.new_state()
+    stepper = b_env.host_stepper(sb)
+    rng = np.random.RandomState(8)
+    terminals = 0
+    for t in range(90):
+        counts_a, ids_a = a_env.valid_actions(sa)
+        counts = stepper.legal().copy()
+        assert (counts == counts_a.cpu().numpy()).all(), t
+        choice = np.where(counts > 0, rng.randint(0, 1 << 30, size=B) % np.maximum(counts, 1), -1).astype(np.int32)
+        choice[t % B] = counts[t % B] + 3                      # past the end of the list: a pass
+        ids = ids_a.cpu().numpy()
+        acts = np.where((choice >= 0) & (choice < counts), ids[np.arange(B), np.clip(choice, 0, ids.shape[1] - 1)], -1).astype(np.int32)
+        sa, pa, ra, ta, wa = a_env.next_state(sa, pa, torch.from_numpy(acts))
+        stepper.choice_np[...] = choice
+        rec = stepper.step()
+        assert (rec == sa.result.cpu().numpy()).all(), t
+        terminals += int(ta.sum())
+    assert terminals > 0 and (sa.packed == sb.packed).all()
